@@ -1,0 +1,94 @@
+// Internal declarations shared by the translation units of libshb200.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/shb200.h"
+
+namespace shb {
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define SHB_CUDA(call)                                                      \
+    do {                                                                    \
+        cudaError_t _e = (call);                                            \
+        if (_e != cudaSuccess) return shb::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+// packed m-major position of (n,m): same indexing as the reference's P_nm table (Legendre_nm.hpp:25-29)
+__host__ __device__ inline int64_t tri(int n, int m, int nmax) {
+    return (int64_t)m * (nmax + 1) - ((int64_t)m * (m + 1)) / 2 + n;
+}
+inline int64_t tri_size(int nmax) { return (int64_t)(nmax + 1) * (nmax + 2) / 2; }
+
+struct DevTables {
+    // Legendre recursion
+    const double* wnm;    // [tri_size]   sqrt((2n+1)/(n+m)*(2n-1)/(n-m))       (Legendre_nm.hpp:73-78)
+    const double* a_nm;   // [tri_size]   = wnm                                  (fast recursion)
+    const double* b_nm;   // [tri_size]   = wnm[n]/wnm[n-1]                      (fast recursion, division-free)
+    const double* cost;   // [nrows]      sin(lat*pi/180) of the primary row     (Ynm.hpp:109)
+    const double* sect;   // [(nmax+1)*nrows] sectorial multiplier of order m    (Legendre_nm.hpp:101,127)
+    const double* pmm;    // [(nmax+1)*nrows] P_mm                               (Legendre_nm.hpp:103,129-130)
+    const int* row_i1;    // [nrows] latitude index of the primary row
+    const int* row_i2;    // [nrows] latitude index of the mirror row or -1
+    const double* w1;     // [nrows] analysis weight of the primary row
+    const double* w2;     // [nrows] analysis weight of the mirror row (0 if none)
+    // longitude stage
+    const double2* tw;    // [K] exp(-2 pi i k / K)
+    const double2* phase; // [nmax+1] exp(+i m lon0)
+    const double* lonr;   // [nlon] lon*pi/180 (dense path; Ynm.hpp:114)
+    // nm packing
+    const int64_t* slot_src;  // [tri_size*2] index into the user nm list for (slot, cos/sin) or -1
+    int nmax, nrows, nlat, nlon, Bp, NC;
+};
+
+struct Plan;
+
+// ---- kernels (launch wrappers; all asynchronous on `st`) --------------------------------------
+// pack: user coefficients -> Cm[tri][NC] ; unpack: Cm -> user (full triangle, position n^2+n+m)
+void launch_pack(const Plan& p, int batch, const double* coef, int64_t cs_b, int64_t cs_nm, cudaStream_t st);
+void launch_unpack(const Plan& p, int batch, double* coef, int64_t cs_b, int64_t cs_nm, cudaStream_t st);
+// Legendre stage
+void launch_legendre_syn(const Plan& p, cudaStream_t st);   // Cm -> G
+void launch_legendre_ana(const Plan& p, cudaStream_t st);   // G  -> Cm
+// longitude stage
+int launch_lon_syn(const Plan& p, int batch, double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, cudaStream_t st);
+int launch_lon_ana(const Plan& p, int batch, const double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, cudaStream_t st);
+int lon_fft_smem_bytes(int K, int ntrans);
+int lon_fft_pick_ntrans(int K, int Bp);
+
+struct Plan {
+    int device = 0, nmax = 0, maxB = 0, Bp = 0, NC = 0;
+    int mode = 0, nlat = 0, nlon = 0, quadrature = 0, flags = 0;
+    int nrows = 0;
+    int64_t nsh = 0;
+    bool full_triangle = true;
+    bool lon_fft = false;
+    bool dmma = false;
+    int K = 0;
+    std::vector<int> radices;
+    int fft_ntrans = 1;
+    int64_t workspace_bytes = 0;
+    DevTables t{};
+    // owned device memory
+    std::vector<void*> owned;
+    double* Cm = nullptr;   // [tri_size][NC]
+    double* G = nullptr;    // [(nmax+1)][nrows][2][NC]
+    // duplicates in the nm list (rare; Ynm.hpp accepts them, dgemv sums them)
+    int64_t ndup = 0;
+    const int64_t* dup_slot = nullptr;  // device [ndup] slot*2+cs
+    const int64_t* dup_src = nullptr;   // device [ndup]
+    // staging for the *_host entry points
+    double* stage_coef = nullptr; int64_t stage_coef_elems = 0;
+    double* stage_grid = nullptr; int64_t stage_grid_elems = 0;
+    cudaStream_t own_stream = nullptr;
+    int launches_syn = 0, launches_ana = 0;
+};
+
+}  // namespace shb
+
+struct shb200_plan { shb::Plan p; };

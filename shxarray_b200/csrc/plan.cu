@@ -1,0 +1,434 @@
+// Transform planner + C ABI of libshb200.so (host side).
+//
+// The planner builds, ON THE HOST with the same libm/IEEE operations the reference uses, every
+// quantity whose rounding matters for parity with shlib:
+//   wnm / wnn square-root tables         Legendre_nm.hpp:68-78
+//   costheta = sin(lat*pi/180)           Ynm.hpp:109
+//   sinTheta = sqrt(1 - costheta^2)      Legendre_nm.hpp:93
+//   sectorial products (1e280 scaling)   Legendre_nm.hpp:101,127-130
+//   alpha = weight*cos(lat*(pi/180))     analysis.pyx:121,129
+// and decides the execution plan: mirror-latitude pairing, FFT vs dense longitude stage, kernel family.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <unordered_map>
+
+#include "internal.h"
+
+namespace shb {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error '%s' in %s (%s:%d)", cudaGetErrorString(e), what, file, line);
+    g_err = buf;
+    return e == cudaErrorMemoryAllocation ? SHB200_ENOMEM : SHB200_ECUDA;
+}
+
+template <typename T>
+static int upload(Plan& p, const std::vector<T>& h, const T** dptr) {
+    void* d = nullptr;
+    size_t bytes = sizeof(T) * (h.empty() ? 1 : h.size());
+    SHB_CUDA(cudaMalloc(&d, bytes));
+    p.owned.push_back(d);
+    p.workspace_bytes += bytes;
+    if (!h.empty()) SHB_CUDA(cudaMemcpy(d, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice));
+    *dptr = (const T*)d;
+    return 0;
+}
+
+static int dev_alloc(Plan& p, size_t bytes, void** out) {
+    void* d = nullptr;
+    SHB_CUDA(cudaMalloc(&d, bytes ? bytes : 8));
+    p.owned.push_back(d);
+    p.workspace_bytes += bytes;
+    *out = d;
+    return 0;
+}
+
+static bool factor235(int K, std::vector<int>& radices) {
+    radices.clear();
+    int k = K;
+    while (k % 4 == 0) { radices.push_back(4); k /= 4; }
+    while (k % 2 == 0) { radices.push_back(2); k /= 2; }
+    while (k % 3 == 0) { radices.push_back(3); k /= 3; }
+    while (k % 5 == 0) { radices.push_back(5); k /= 5; }
+    return k == 1;
+}
+
+static double ulp_scale(double x) { return std::ldexp(1.0, -52) * std::fmax(std::fabs(x), 1.0); }
+
+static int build_plan(const shb200_plan_desc& d, Plan& p) {
+    if (d.nmax < 0 || d.max_batch < 1 || d.nlat < 1 || d.nlon < 1 || !d.lat_deg || !d.lon_deg) {
+        set_error("plan_create: invalid sizes or null coordinate arrays");
+        return SHB200_EINVAL;
+    }
+    if (d.mode == SHB200_MODE_POINTS && d.nlat != d.nlon) {
+        set_error("plan_create: point mode needs nlat == nlon");
+        return SHB200_EINVAL;
+    }
+    if (d.mode == SHB200_MODE_POINTS && d.quadrature != SHB200_QUAD_NONE) {
+        set_error("plan_create: analysis is not defined for point sets");
+        return SHB200_EINVAL;
+    }
+    if (d.quadrature == SHB200_QUAD_LATWEIGHTS && !d.lat_weights) {
+        set_error("plan_create: SHB200_QUAD_LATWEIGHTS needs lat_weights");
+        return SHB200_EINVAL;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device available: libshb200 has no CPU fallback");
+        return SHB200_ECUDA;
+    }
+    if (d.device < 0 || d.device >= ndev) { set_error("plan_create: bad device ordinal"); return SHB200_EINVAL; }
+    SHB_CUDA(cudaSetDevice(d.device));
+
+    p.device = d.device; p.nmax = d.nmax; p.maxB = d.max_batch;
+    p.Bp = (d.max_batch + 3) / 4 * 4;           // columns come in blocks of 8 = (cos,sin) x 4 fields
+    p.NC = 2 * p.Bp;
+    p.mode = d.mode; p.nlat = d.nlat; p.nlon = d.nlon; p.quadrature = d.quadrature; p.flags = d.flags;
+    const int N = d.nmax;
+    const int64_t T = tri_size(N);
+
+    // ---- nm list -> slot map -----------------------------------------------------------------
+    std::vector<int64_t> slot_src((size_t)T * 2, -1);
+    std::vector<int64_t> dup_slot, dup_src;
+    if (d.nsh > 0) {
+        if (!d.n || !d.m) { set_error("plan_create: nsh > 0 but n/m arrays are null"); return SHB200_EINVAL; }
+        p.nsh = d.nsh;
+        p.full_triangle = (d.nsh == (int64_t)(N + 1) * (N + 1));
+        for (int64_t k = 0; k < d.nsh; ++k) {
+            int n = d.n[k], m = d.m[k], am = m < 0 ? -m : m;
+            if (n < 0 || n > N || am > n) { set_error("plan_create: (n,m) entry out of range"); return SHB200_EINVAL; }
+            int64_t s = tri(n, am, N) * 2 + (m < 0 ? 1 : 0);
+            if (slot_src[s] < 0) slot_src[s] = k;
+            else { dup_slot.push_back(s); dup_src.push_back(k); }
+            if (p.full_triangle && k != (int64_t)n * n + n + m) p.full_triangle = false;
+        }
+    } else {
+        p.nsh = (int64_t)(N + 1) * (N + 1);
+        p.full_triangle = true;
+        for (int n = 0; n <= N; ++n)
+            for (int m = -n; m <= n; ++m) {
+                int am = m < 0 ? -m : m;
+                slot_src[tri(n, am, N) * 2 + (m < 0 ? 1 : 0)] = (int64_t)n * n + n + m;
+            }
+    }
+
+    // ---- Legendre tables (bit-identical to Legendre_nm.hpp:68-78) ------------------------------
+    std::vector<double> wnn(N + 2, 0.0), wnm((size_t)T, 0.0), bnm((size_t)T, 0.0);
+    if (N >= 1) wnn[1] = sqrt(3.0);
+    for (int n = 2; n <= N; ++n) wnn[n] = sqrt((2 * n + 1) / (2.0 * n));
+    for (int m = 0; m <= N; ++m)
+        for (int n = m + 1; n <= N; ++n)
+            wnm[tri(n, m, N)] = sqrt((2 * n + 1.0) / (n + m) * (2 * n - 1.0) / (n - m));
+    for (int m = 0; m <= N; ++m)
+        for (int n = m + 2; n <= N; ++n) bnm[tri(n, m, N)] = wnm[tri(n, m, N)] / wnm[tri(n - 1, m, N)];
+
+    // ---- latitude rows: mirror pairing ---------------------------------------------------------
+    std::vector<double> cost_lat(d.nlat);
+    for (int i = 0; i < d.nlat; ++i) cost_lat[i] = sin(d.lat_deg[i] * M_PI / 180.0);  // Ynm.hpp:109
+    std::vector<int> i1, i2;
+    {
+        std::vector<char> used(d.nlat, 0);
+        std::unordered_multimap<uint64_t, int> bybits;
+        const bool pair_ok = d.mode == SHB200_MODE_GRID && !(d.flags & SHB200_FLAG_NO_SYMMETRY);
+        if (pair_ok)
+            for (int i = 0; i < d.nlat; ++i) {
+                uint64_t b; memcpy(&b, &cost_lat[i], 8);
+                bybits.emplace(b, i);
+            }
+        for (int i = 0; i < d.nlat; ++i) {
+            if (used[i]) continue;
+            used[i] = 1;
+            int mate = -1;
+            if (pair_ok && cost_lat[i] != 0.0) {
+                double neg = -cost_lat[i];
+                uint64_t b; memcpy(&b, &neg, 8);
+                auto range = bybits.equal_range(b);
+                for (auto it = range.first; it != range.second; ++it)
+                    if (!used[it->second]) { mate = it->second; break; }
+            }
+            if (mate >= 0) used[mate] = 1;
+            i1.push_back(i); i2.push_back(mate);
+        }
+    }
+    p.nrows = (int)i1.size();
+    const int R = p.nrows;
+    std::vector<double> cost(R), w1(R, 0.0), w2(R, 0.0);
+    for (int r = 0; r < R; ++r) cost[r] = cost_lat[i1[r]];
+    if (d.quadrature != SHB200_QUAD_NONE) {
+        const double d2r = M_PI / 180;  // analysis.pyx:121
+        auto wrow = [&](int i) {
+            return d.quadrature == SHB200_QUAD_SHLIB ? d.weight * cos(d.lat_deg[i] * d2r)  // analysis.pyx:129
+                                                     : d.weight * d.lat_weights[i];
+        };
+        for (int r = 0; r < R; ++r) { w1[r] = wrow(i1[r]); w2[r] = i2[r] >= 0 ? wrow(i2[r]) : 0.0; }
+    }
+    // sectorial multipliers per (order, row): Legendre_nm.hpp:93,101,127-130
+    std::vector<double> sect((size_t)(N + 1) * R), pmm((size_t)(N + 1) * R);
+    {
+        const double tiny = 1e-280;
+        for (int r = 0; r < R; ++r) {
+            double c = cost[r];
+            double sint = sqrt(1 - c * c);
+            double s = 1.0 / tiny;
+            sect[r] = s; pmm[r] = 1.0;
+            for (int m = 0; m < N; ++m) {
+                s *= wnn[m + 1] * sint;
+                sect[(size_t)(m + 1) * R + r] = s;
+                pmm[(size_t)(m + 1) * R + r] = s * tiny;
+            }
+        }
+    }
+
+    // ---- longitude stage decision ------------------------------------------------------------
+    p.K = d.nlon;
+    p.lon_fft = false;
+    double lon0 = d.lon_deg[0];
+    if (d.mode == SHB200_MODE_GRID && !(d.flags & SHB200_FLAG_DENSE_LON) && d.nlon >= 2 && factor235(d.nlon, p.radices)) {
+        bool uniform = true;
+        long double step = 360.0L / d.nlon;
+        for (int j = 0; j < d.nlon && uniform; ++j) {
+            long double ideal = (long double)lon0 + j * step;
+            if (fabsl((long double)d.lon_deg[j] - ideal) > 8.0L * ulp_scale(d.lon_deg[j])) uniform = false;
+        }
+        if (uniform) {
+            p.fft_ntrans = lon_fft_pick_ntrans(p.K, p.Bp);
+            if (p.fft_ntrans >= 1) p.lon_fft = true;
+        }
+    }
+    std::vector<double2> tw, phase;
+    std::vector<double> lonr(d.nlon);
+    for (int j = 0; j < d.nlon; ++j) lonr[j] = d.lon_deg[j] * M_PI / 180.0;  // Ynm.hpp:114
+    if (p.lon_fft) {
+        tw.resize(p.K);
+        const long double twopi = 6.283185307179586476925286766559L;
+        for (int k = 0; k < p.K; ++k) {
+            // exact octant reduction keeps the table accurate to <1 ulp
+            long double a = twopi * (long double)k / (long double)p.K;
+            tw[k] = make_double2((double)cosl(a), (double)-sinl(a));
+        }
+        if (p.K % 4 == 0) { tw[p.K / 4] = make_double2(0.0, -1.0); tw[p.K / 2] = make_double2(-1.0, 0.0); tw[3 * p.K / 4] = make_double2(0.0, 1.0); }
+        else if (p.K % 2 == 0) tw[p.K / 2] = make_double2(-1.0, 0.0);
+        phase.resize(N + 1);
+        long double l0 = (long double)lon0 * (3.141592653589793238462643383279503L / 180.0L);
+        for (int m = 0; m <= N; ++m) {
+            long double a = fmodl((long double)m * l0, twopi);
+            phase[m] = make_double2((double)cosl(a), (double)sinl(a));
+        }
+    }
+
+    // ---- kernel family -----------------------------------------------------------------------
+    p.dmma = !(d.flags & SHB200_FLAG_NO_DMMA);
+
+    // ---- upload ------------------------------------------------------------------------------
+    int rc;
+    DevTables& t = p.t;
+    if ((rc = upload(p, wnm, &t.wnm))) return rc;
+    t.a_nm = t.wnm;
+    if ((rc = upload(p, bnm, &t.b_nm))) return rc;
+    if ((rc = upload(p, cost, &t.cost))) return rc;
+    if ((rc = upload(p, sect, &t.sect))) return rc;
+    if ((rc = upload(p, pmm, &t.pmm))) return rc;
+    if ((rc = upload(p, i1, &t.row_i1))) return rc;
+    if ((rc = upload(p, i2, &t.row_i2))) return rc;
+    if ((rc = upload(p, w1, &t.w1))) return rc;
+    if ((rc = upload(p, w2, &t.w2))) return rc;
+    if ((rc = upload(p, tw, &t.tw))) return rc;
+    if ((rc = upload(p, phase, &t.phase))) return rc;
+    if ((rc = upload(p, lonr, &t.lonr))) return rc;
+    if ((rc = upload(p, slot_src, &t.slot_src))) return rc;
+    p.ndup = (int64_t)dup_slot.size();
+    if ((rc = upload(p, dup_slot, &p.dup_slot))) return rc;
+    if ((rc = upload(p, dup_src, &p.dup_src))) return rc;
+    t.nmax = N; t.nrows = R; t.nlat = d.nlat; t.nlon = d.nlon; t.Bp = p.Bp; t.NC = p.NC;
+
+    void* ptr;
+    if ((rc = dev_alloc(p, sizeof(double) * (size_t)T * p.NC, &ptr))) return rc;
+    p.Cm = (double*)ptr;
+    if ((rc = dev_alloc(p, sizeof(double) * (size_t)(N + 1) * R * 2 * p.NC, &ptr))) return rc;
+    p.G = (double*)ptr;
+    SHB_CUDA(cudaMemset(p.Cm, 0, sizeof(double) * (size_t)T * p.NC));
+    SHB_CUDA(cudaMemset(p.G, 0, sizeof(double) * (size_t)(N + 1) * R * 2 * p.NC));
+    SHB_CUDA(cudaStreamCreateWithFlags(&p.own_stream, cudaStreamNonBlocking));
+    p.launches_syn = 3 + (p.ndup ? 1 : 0);
+    p.launches_ana = 3;
+    return 0;
+}
+
+static void free_plan(Plan& p) {
+    cudaSetDevice(p.device);
+    for (void* d : p.owned) cudaFree(d);
+    p.owned.clear();
+    if (p.stage_coef) cudaFree(p.stage_coef);
+    if (p.stage_grid) cudaFree(p.stage_grid);
+    if (p.own_stream) cudaStreamDestroy(p.own_stream);
+}
+
+static int check_batch(const Plan& p, int batch) {
+    if (batch < 1 || batch > p.maxB) { set_error("batch must be in [1, max_batch] of the plan"); return SHB200_EINVAL; }
+    return 0;
+}
+
+}  // namespace shb
+
+using namespace shb;
+
+extern "C" {
+
+int shb200_version(void) { return SHB200_VERSION; }
+const char* shb200_last_error(void) { return g_err.c_str(); }
+
+int shb200_plan_create(const shb200_plan_desc* desc, shb200_plan** out) {
+    if (!desc || !out || desc->struct_size != (int32_t)sizeof(shb200_plan_desc)) {
+        set_error("plan_create: null argument or struct_size mismatch");
+        return SHB200_EINVAL;
+    }
+    shb200_plan* h = new shb200_plan();
+    int rc = build_plan(*desc, h->p);
+    if (rc) { free_plan(h->p); delete h; *out = nullptr; return rc; }
+    *out = h;
+    return 0;
+}
+
+void shb200_plan_destroy(shb200_plan* plan) {
+    if (!plan) return;
+    free_plan(plan->p);
+    delete plan;
+}
+
+int shb200_plan_get_info(const shb200_plan* plan, shb200_plan_info* info) {
+    if (!plan || !info) { set_error("plan_get_info: null argument"); return SHB200_EINVAL; }
+    const Plan& p = plan->p;
+    info->nmax = p.nmax; info->max_batch = p.maxB; info->padded_batch = p.Bp;
+    info->nlat = p.nlat; info->nlon = p.nlon; info->nrows = p.nrows;
+    info->lon_fft = p.lon_fft ? 1 : 0; info->dmma = p.dmma ? 1 : 0;
+    info->nsh = p.nsh; info->nsh_full = (int64_t)(p.nmax + 1) * (p.nmax + 1);
+    info->workspace_bytes = p.workspace_bytes;
+    info->launches_synthesis = p.launches_syn; info->launches_analysis = p.launches_ana;
+    return 0;
+}
+
+int shb200_synthesis(shb200_plan* plan, int32_t batch, const double* coef, int64_t cs_b, int64_t cs_nm,
+                     double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, void* stream) {
+    if (!plan || !coef || !grid) { set_error("synthesis: null argument"); return SHB200_EINVAL; }
+    Plan& p = plan->p;
+    int rc = check_batch(p, batch);
+    if (rc) return rc;
+    SHB_CUDA(cudaSetDevice(p.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    launch_pack(p, batch, coef, cs_b, cs_nm, st);
+    launch_legendre_syn(p, st);
+    rc = launch_lon_syn(p, batch, grid, gs_b, gs_lat, gs_lon, st);
+    if (rc) return rc;
+    SHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int shb200_analysis(shb200_plan* plan, int32_t batch, const double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon,
+                    double* coef, int64_t cs_b, int64_t cs_nm, void* stream) {
+    if (!plan || !coef || !grid) { set_error("analysis: null argument"); return SHB200_EINVAL; }
+    Plan& p = plan->p;
+    if (p.quadrature == SHB200_QUAD_NONE) { set_error("analysis: plan was created without quadrature weights"); return SHB200_EINVAL; }
+    int rc = check_batch(p, batch);
+    if (rc) return rc;
+    SHB_CUDA(cudaSetDevice(p.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = launch_lon_ana(p, batch, grid, gs_b, gs_lat, gs_lon, st);
+    if (rc) return rc;
+    launch_legendre_ana(p, st);
+    launch_unpack(p, batch, coef, cs_b, cs_nm, st);
+    SHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// extent (in elements) spanned by a strided 2-D / 3-D array
+static int64_t span2(int64_t n0, int64_t s0, int64_t n1, int64_t s1) { return (n0 - 1) * llabs(s0) + (n1 - 1) * llabs(s1) + 1; }
+
+static int ensure_stage(double** buf, int64_t* have, int64_t need) {
+    if (*have >= need) return 0;
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr; *have = 0;
+    SHB_CUDA(cudaMalloc((void**)buf, sizeof(double) * need));
+    *have = need;
+    return 0;
+}
+
+int shb200_synthesis_host(shb200_plan* plan, int32_t batch, const double* coef, int64_t cs_b, int64_t cs_nm,
+                          double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon) {
+    if (!plan || !coef || !grid) { set_error("synthesis_host: null argument"); return SHB200_EINVAL; }
+    Plan& p = plan->p;
+    int rc = check_batch(p, batch);
+    if (rc) return rc;
+    if (cs_b < 0 || cs_nm < 0 || gs_b < 0 || gs_lat < 0 || gs_lon < 0) { set_error("host entry points need non-negative strides"); return SHB200_EINVAL; }
+    SHB_CUDA(cudaSetDevice(p.device));
+    int64_t ncoef = span2(batch, cs_b, p.nsh, cs_nm);
+    bool points = p.mode == SHB200_MODE_POINTS;
+    int64_t ngrid = points ? span2(batch, gs_b, p.nlat, gs_lat) : span2(batch, gs_b, p.nlat, gs_lat) + (p.nlon - 1) * gs_lon;
+    if ((rc = ensure_stage(&p.stage_coef, &p.stage_coef_elems, ncoef))) return rc;
+    if ((rc = ensure_stage(&p.stage_grid, &p.stage_grid_elems, ngrid))) return rc;
+    SHB_CUDA(cudaMemcpyAsync(p.stage_coef, coef, sizeof(double) * ncoef, cudaMemcpyHostToDevice, p.own_stream));
+    rc = shb200_synthesis(plan, batch, p.stage_coef, cs_b, cs_nm, p.stage_grid, gs_b, gs_lat, gs_lon, p.own_stream);
+    if (rc) return rc;
+    SHB_CUDA(cudaMemcpyAsync(grid, p.stage_grid, sizeof(double) * ngrid, cudaMemcpyDeviceToHost, p.own_stream));
+    SHB_CUDA(cudaStreamSynchronize(p.own_stream));
+    return 0;
+}
+
+int shb200_analysis_host(shb200_plan* plan, int32_t batch, const double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon,
+                         double* coef, int64_t cs_b, int64_t cs_nm) {
+    if (!plan || !coef || !grid) { set_error("analysis_host: null argument"); return SHB200_EINVAL; }
+    Plan& p = plan->p;
+    int rc = check_batch(p, batch);
+    if (rc) return rc;
+    if (cs_b < 0 || cs_nm < 0 || gs_b < 0 || gs_lat < 0 || gs_lon < 0) { set_error("host entry points need non-negative strides"); return SHB200_EINVAL; }
+    SHB_CUDA(cudaSetDevice(p.device));
+    int64_t nfull = (int64_t)(p.nmax + 1) * (p.nmax + 1);
+    int64_t ncoef = span2(batch, cs_b, nfull, cs_nm);
+    int64_t ngrid = span2(batch, gs_b, p.nlat, gs_lat) + (p.nlon - 1) * gs_lon;
+    if ((rc = ensure_stage(&p.stage_coef, &p.stage_coef_elems, ncoef))) return rc;
+    if ((rc = ensure_stage(&p.stage_grid, &p.stage_grid_elems, ngrid))) return rc;
+    SHB_CUDA(cudaMemcpyAsync(p.stage_grid, grid, sizeof(double) * ngrid, cudaMemcpyHostToDevice, p.own_stream));
+    rc = shb200_analysis(plan, batch, p.stage_grid, gs_b, gs_lat, gs_lon, p.stage_coef, cs_b, cs_nm, p.own_stream);
+    if (rc) return rc;
+    SHB_CUDA(cudaMemcpyAsync(coef, p.stage_coef, sizeof(double) * ncoef, cudaMemcpyDeviceToHost, p.own_stream));
+    SHB_CUDA(cudaStreamSynchronize(p.own_stream));
+    return 0;
+}
+
+// Gauss-Legendre nodes/weights by Newton iteration on P_n in long double.
+int shb200_gauss_nodes(int32_t n, double* x, double* w) {
+    if (n < 1 || !x || !w) { set_error("gauss_nodes: invalid argument"); return SHB200_EINVAL; }
+    const long double pi = 3.141592653589793238462643383279503L;
+    for (int i = 0; i < (n + 1) / 2; ++i) {
+        long double z = cosl(pi * (i + 0.75L) / (n + 0.5L));  // i-th root from the north
+        long double pp = 1;
+        for (int it = 0; it < 100; ++it) {
+            long double p1 = 1, p2 = 0;
+            for (int j = 1; j <= n; ++j) {
+                long double p3 = p2; p2 = p1;
+                p1 = ((2 * j - 1) * z * p2 - (j - 1) * p3) / j;
+            }
+            pp = n * (z * p1 - p2) / (z * z - 1);
+            long double dz = p1 / pp;
+            z -= dz;
+            if (fabsl(dz) < 1e-19L) break;
+        }
+        {   // derivative at the converged root
+            long double p1 = 1, p2 = 0;
+            for (int j = 1; j <= n; ++j) { long double p3 = p2; p2 = p1; p1 = ((2 * j - 1) * z * p2 - (j - 1) * p3) / j; }
+            pp = n * (z * p1 - p2) / (z * z - 1);
+        }
+        long double wi = 2 / ((1 - z * z) * pp * pp);
+        // ascending latitude: south first
+        x[i] = (double)-z; x[n - 1 - i] = (double)z;
+        w[i] = (double)wi; w[n - 1 - i] = (double)wi;
+    }
+    if (n % 2) x[n / 2] = 0.0;
+    return 0;
+}
+
+}  // extern "C"

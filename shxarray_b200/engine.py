@@ -1,0 +1,339 @@
+"""numpy / torch level host API of the B200 engine (no xarray needed).
+
+Mirrors what the reference's ``Synthesis`` / ``Analysis`` operators do with raw arrays
+(src/builtin_backend/synthesis.pyx:76-189, analysis.pyx:31-139) but hands the WHOLE batch to the
+device in one call (the per-field Python loop of shtns.py:255-259 is what this engine avoids).
+
+* numpy inputs  -> ``shb200_*_host`` (host->device copy, kernels, device->host copy inside the call)
+* torch CUDA tensors -> ``shb200_synthesis`` / ``shb200_analysis`` on torch's current stream; torch is
+  used purely as the owner of device memory.
+"""
+import hashlib
+import threading
+
+import numpy as np
+
+from . import capi
+
+
+def nm_index(nmax, nmin=0):
+    """(n, m) int32 arrays in shxarray's nm order: n-major, m=-n..n (sh_indexing.py:66)."""
+    n = np.concatenate([np.full(2 * k + 1, k, dtype=np.int32) for k in range(nmin, nmax + 1)])
+    m = np.concatenate([np.arange(-k, k + 1, dtype=np.int32) for k in range(nmin, nmax + 1)])
+    return n, m
+
+
+def _nice_nlon(nmin):
+    """smallest 2^a * {1,3,5,9,15} >= nmin (FFT-friendly longitude count)."""
+    best = None
+    for odd in (1, 3, 5, 9, 15):
+        k = odd
+        while k < nmin:
+            k *= 2
+        best = k if best is None or k < best else best
+    return best
+
+
+def lonlat_grid(nmax=None, lon=None, lat=None, gtype=None):
+    """Grid generator.  'regular' / 'regular_lon0' reproduce shlib.pyx:87-96 exactly; 'gauss' is a
+    Gauss-Legendre grid (nlat = nmax+1 rounded up to a multiple of 4, nlon FFT-friendly >= 2nmax+2).
+    Returns dict(lon=, lat=, gtype=, lat_weights= (gauss only))."""
+    if gtype is None:
+        gtype = "gauss"
+    if gtype not in ("regular", "regular_lon0", "gauss", "point"):
+        raise ValueError("Only 'gauss', 'regular', 'regular_lon0' and 'point' grid types are supported")
+    if nmax is not None:
+        if lon is not None or lat is not None:
+            raise ValueError("If nmax is specified, lon and lat should not be specified")
+        if gtype in ("regular", "regular_lon0"):
+            idres = 1
+            while idres > 360 / nmax / 4:
+                idres = idres / 2
+            lon = np.arange(-180 + idres / 2, 180, idres) if gtype == "regular" else np.arange(0, 360, idres)
+            lat = np.arange(-90 + idres / 2, 90, idres)
+            return dict(lon=lon, lat=lat, gtype=gtype)
+        if gtype == "gauss":
+            nlat = (nmax + 1 + 3) // 4 * 4
+            nlon = _nice_nlon(2 * nmax + 2)
+            x, w = capi.gauss_nodes(nlat)
+            latv = np.rad2deg(np.arcsin(x))
+            half = nlat // 2
+            latv[nlat - half:] = -latv[:half][::-1]   # bit-exact mirror symmetry
+            return dict(lon=np.arange(nlon) * (360.0 / nlon), lat=latv, gtype=gtype, lat_weights=w)
+        raise ValueError("a 'point' grid needs explicit lon and lat")
+    if lon is None or lat is None:
+        raise ValueError("Either nmax or lon and lat should be specified")
+    lon = np.asarray(lon, dtype=np.float64)
+    lat = np.asarray(lat, dtype=np.float64)
+    if gtype == "point" and len(lon) != len(lat):
+        raise ValueError("For point type 'grid', lon and lat should have the same length")
+    return dict(lon=lon, lat=lat, gtype=gtype)
+
+
+def uniform_step(x):
+    """cf.py:25-30: the step if np.diff has min == max exactly, else None."""
+    d = np.diff(np.asarray(x, dtype=np.float64))
+    if len(d) == 0:
+        return None
+    return float(d.min()) if d.min() == d.max() else None
+
+
+def analysis_weight_shlib(lon, lat):
+    """|stepx*stepy|/(4 pi) evaluated like analysis.pyx:57-60."""
+    sx, sy = uniform_step(lon), uniform_step(lat)
+    if sx is None or sy is None:
+        raise RuntimeError("grid is not equidistant in lon and lat directions")
+    stepx = sx * np.pi / 180
+    stepy = sy * np.pi / 180
+    return float(abs(stepx * stepy) / (4 * np.pi))
+
+
+def gauss_lat_weights(lat):
+    """Gauss-Legendre weights for a latitude vector that consists of the nlat Gauss nodes (either order)."""
+    lat = np.asarray(lat, dtype=np.float64)
+    x, w = capi.gauss_nodes(len(lat))
+    s = np.sin(np.deg2rad(lat))
+    if np.allclose(s, x, rtol=0, atol=1e-10):
+        return w
+    if np.allclose(s, x[::-1], rtol=0, atol=1e-10):
+        return w[::-1].copy()
+    raise RuntimeError("latitudes are not the Gauss-Legendre nodes of this size; cannot use gauss quadrature")
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _digest(*arrays):
+    h = hashlib.blake2b(digest_size=16)
+    for a in arrays:
+        if a is None:
+            h.update(b"-")
+        else:
+            a = np.ascontiguousarray(a)
+            h.update(str(a.dtype).encode() + str(a.shape).encode())
+            h.update(a.tobytes())
+    return h.hexdigest()
+
+
+class SHEngine:
+    """Plan cache + array front-end.  One instance per process/device is enough (plans are reused)."""
+
+    #: device memory budget for one plan's workspace (bytes); larger batches are processed in chunks
+    WORKSPACE_BUDGET = 48 << 30
+
+    def __init__(self, device=0, flags=0):
+        self.device = int(device)
+        self.flags = int(flags)
+        self._plans = {}
+        self._lock = threading.Lock()
+        self.launches = 0   # kernels launched by this engine (gpu_launches accounting in bench.py)
+
+    # ------------------------------------------------------------------------------------------
+    def _chunk(self, nmax, nrows_guess, batch):
+        tri = (nmax + 1) * (nmax + 2) // 2
+        per_field = 16 * tri + 32 * (nmax + 1) * nrows_guess
+        return int(max(1, min(batch, self.WORKSPACE_BUDGET // max(per_field, 1))))
+
+    def get_plan(self, nmax, lat, lon, batch, n=None, m=None, mode=capi.MODE_GRID, quadrature=capi.QUAD_NONE,
+                 weight=0.0, lat_weights=None, flags=None):
+        flags = self.flags if flags is None else flags
+        maxb = self._chunk(nmax, len(lat), batch)
+        key = (nmax, mode, quadrature, float(weight), flags, _digest(lat, lon, n, m, lat_weights))
+        with self._lock:
+            plan = self._plans.get(key)
+            if plan is not None and plan.max_batch >= maxb:
+                return plan
+            if plan is not None:
+                plan.close()
+            plan = capi.Plan(nmax, lat, lon, max_batch=maxb, n=n, m=m, mode=mode, quadrature=quadrature,
+                             weight=weight, lat_weights=lat_weights, flags=flags, device=self.device)
+            self._plans[key] = plan
+            return plan
+
+    def clear(self):
+        with self._lock:
+            for p in self._plans.values():
+                p.close()
+            self._plans.clear()
+
+    # ------------------------------------------------------------------------------------------
+    def synthesis(self, coef, n=None, m=None, lon=None, lat=None, nmax=None, points=False, nm_axis=-1,
+                  layout="batch_first", out=None, flags=None):
+        """Spherical-harmonic synthesis of a batch of coefficient vectors.
+
+        coef : [B, nsh] (``nm_axis=-1``) or [nsh, B] (``nm_axis=0``) or [nsh]; numpy (host) or torch CUDA tensor.
+        n, m : degree/order of each coefficient (any subset/order; m<0 = sine).  None => full triangle
+               in nm order for ``nmax``.
+        lon, lat : degrees.  ``points=True``: paired points (synthesis.pyx:186-189) else tensor grid.
+        layout : 'batch_first' -> [B, nlat, nlon] ; 'shlib' -> [nlat, nlon, B] (synthesis.pyx:68-71).
+        """
+        lon = np.ascontiguousarray(lon, dtype=np.float64)
+        lat = np.ascontiguousarray(lat, dtype=np.float64)
+        if n is None:
+            if nmax is None:
+                raise ValueError("either (n, m) or nmax must be given")
+            nsh = (nmax + 1) ** 2
+        else:
+            n = np.ascontiguousarray(n, dtype=np.int32)
+            m = np.ascontiguousarray(m, dtype=np.int32)
+            nsh = len(n)
+            nmax = int(n.max()) if nmax is None else int(nmax)
+        tor = _is_torch(coef)
+        if not tor:
+            coef = np.asarray(coef)
+            if coef.dtype != np.float64:
+                coef = coef.astype(np.float64)
+        elif str(coef.dtype) != "torch.float64":
+            raise TypeError("coefficients must be float64")
+        squeeze = coef.ndim == 1
+        if squeeze:
+            coef = coef.reshape(1, nsh) if nm_axis in (-1, 0) else coef
+            nm_axis = -1
+        if coef.ndim != 2:
+            raise ValueError("coef must be 1-D or 2-D ([B, nsh] or [nsh, B])")
+        if nm_axis in (-1, 1):
+            B = coef.shape[0]
+        elif nm_axis == 0:
+            coef = coef.T
+            B = coef.shape[0]
+        else:
+            raise ValueError("nm_axis must be 0 or -1")
+        if coef.shape[1] != nsh:
+            raise ValueError(f"coefficient axis has {coef.shape[1]} entries, nm list has {nsh}")
+        mode = capi.MODE_POINTS if points else capi.MODE_GRID
+        if points and len(lon) != len(lat):
+            raise ValueError("point synthesis needs equally sized lon and lat")
+        plan = self.get_plan(nmax, lat, lon, B, n=n, m=m, mode=mode, flags=flags)
+        L, K = len(lat), len(lon)
+        if points:
+            shape = (B, L) if layout == "batch_first" else (L, B)
+        else:
+            shape = (B, L, K) if layout == "batch_first" else (L, K, B)
+        if tor:
+            import torch
+            if out is None:
+                out = torch.empty(shape, dtype=torch.float64, device=coef.device)
+            es = lambda t: [s for s in t.stride()]
+            ptr = lambda t: t.data_ptr()
+            stream = torch.cuda.current_stream(coef.device).cuda_stream
+        else:
+            if out is None:
+                out = np.empty(shape, dtype=np.float64)
+            es = lambda a: [s // 8 for s in a.strides]
+            ptr = lambda a: a.ctypes.data
+            stream = None
+        os_ = es(out)
+        if points:
+            gs_b, gs_lat, gs_lon = (os_[0], os_[1], 0) if layout == "batch_first" else (os_[1], os_[0], 0)
+        else:
+            gs_b, gs_lat, gs_lon = (os_[0], os_[1], os_[2]) if layout == "batch_first" else (os_[2], os_[0], os_[1])
+        cs = es(coef)
+        step = plan.max_batch
+        for b0 in range(0, B, step):
+            nb = min(step, B - b0)
+            cptr = ptr(coef) + 8 * b0 * cs[0]
+            gptr = ptr(out) + 8 * b0 * gs_b
+            if tor:
+                plan.synthesis_dev(nb, cptr, cs[0], cs[1], gptr, gs_b, gs_lat, gs_lon, stream)
+            else:
+                plan.synthesis_host(nb, cptr, cs[0], cs[1], gptr, gs_b, gs_lat, gs_lon)
+            self.launches += plan.info.launches_synthesis
+        if squeeze:
+            out = out[0] if layout == "batch_first" else out[..., 0]
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    def analysis(self, grid, nmax, lon, lat, quadrature="shlib", lat_weights=None, weight=None, layout="batch_first",
+                 out=None, flags=None):
+        """Spherical-harmonic analysis of a batch of lon/lat grids (analysis.pyx:31-139).
+
+        grid : [B, nlat, nlon] ('batch_first') or [nlat, nlon, B] ('shlib'); any strides; numpy or torch CUDA.
+        quadrature : 'shlib'  -> midpoint rule weight*cos(lat) on a uniform grid (parity with shlib),
+                     'gauss'  -> Gauss-Legendre weights (lat must be the Gauss nodes),
+                     'weights'-> ``weight * lat_weights[i]``.
+        Returns [B, (nmax+1)^2] in nm order (n-major, m=-n..n), nmin=0 (analysis.pyx:29).
+        """
+        lon = np.ascontiguousarray(lon, dtype=np.float64)
+        lat = np.ascontiguousarray(lat, dtype=np.float64)
+        tor = _is_torch(grid)
+        if not tor:
+            grid = np.asarray(grid)
+            if grid.dtype != np.float64:
+                grid = grid.astype(np.float64)
+        elif str(grid.dtype) != "torch.float64":
+            raise TypeError("grid must be float64")
+        squeeze = grid.ndim == 2
+        if squeeze:
+            grid = grid[None] if layout == "batch_first" else grid[..., None]
+        if grid.ndim != 3:
+            raise ValueError("grid must be [B, nlat, nlon] or [nlat, nlon, B]")
+        L, K = len(lat), len(lon)
+        if layout == "batch_first":
+            B = grid.shape[0]
+            ok = grid.shape[1] == L and grid.shape[2] == K
+        else:
+            B = grid.shape[2]
+            ok = grid.shape[0] == L and grid.shape[1] == K
+        if not ok:
+            raise ValueError("grid shape does not match lon/lat")
+        if quadrature == "shlib":
+            q, wgt, lw = capi.QUAD_SHLIB, analysis_weight_shlib(lon, lat), None
+        elif quadrature == "gauss":
+            q, wgt, lw = capi.QUAD_LATWEIGHTS, 1.0 / (2.0 * K), gauss_lat_weights(lat)
+        elif quadrature == "weights":
+            q, wgt, lw = capi.QUAD_LATWEIGHTS, (1.0 if weight is None else float(weight)), np.asarray(lat_weights, dtype=np.float64)
+        else:
+            raise ValueError("quadrature must be 'shlib', 'gauss' or 'weights'")
+        plan = self.get_plan(nmax, lat, lon, B, quadrature=q, weight=wgt, lat_weights=lw, flags=flags)
+        nsh = (nmax + 1) ** 2
+        if tor:
+            import torch
+            if out is None:
+                out = torch.empty((B, nsh), dtype=torch.float64, device=grid.device)
+            es = lambda t: [s for s in t.stride()]
+            ptr = lambda t: t.data_ptr()
+            stream = torch.cuda.current_stream(grid.device).cuda_stream
+        else:
+            if out is None:
+                out = np.empty((B, nsh), dtype=np.float64)
+            es = lambda a: [s // 8 for s in a.strides]
+            ptr = lambda a: a.ctypes.data
+            stream = None
+        gs = es(grid)
+        gs_b, gs_lat, gs_lon = (gs[0], gs[1], gs[2]) if layout == "batch_first" else (gs[2], gs[0], gs[1])
+        cs = es(out)
+        if not tor and min(gs_b, gs_lat, gs_lon) < 0:
+            grid = np.ascontiguousarray(grid)
+            gs = es(grid)
+            gs_b, gs_lat, gs_lon = (gs[0], gs[1], gs[2]) if layout == "batch_first" else (gs[2], gs[0], gs[1])
+        step = plan.max_batch
+        for b0 in range(0, B, step):
+            nb = min(step, B - b0)
+            gptr = ptr(grid) + 8 * b0 * gs_b
+            cptr = ptr(out) + 8 * b0 * cs[0]
+            if tor:
+                plan.analysis_dev(nb, gptr, gs_b, gs_lat, gs_lon, cptr, cs[0], cs[1], stream)
+            else:
+                plan.analysis_host(nb, gptr, gs_b, gs_lat, gs_lon, cptr, cs[0], cs[1])
+            self.launches += plan.info.launches_analysis
+        if squeeze:
+            out = out[0]
+        return out
+
+
+_default = {}
+
+
+def default_engine(device=0):
+    if device not in _default:
+        _default[device] = SHEngine(device)
+    return _default[device]
+
+
+def synthesis(coef, n=None, m=None, lon=None, lat=None, **kw):
+    return default_engine(kw.pop("device", 0)).synthesis(coef, n, m, lon, lat, **kw)
+
+
+def analysis(grid, nmax, lon, lat, **kw):
+    return default_engine(kw.pop("device", 0)).analysis(grid, nmax, lon, lat, **kw)

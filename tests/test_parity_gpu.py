@@ -1,0 +1,251 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle, the committed golden vectors
+and the reference's own known answers.  Metric: per-field max|d|/max|ref| <= 1e-12 (BASELINE.json north_star).
+
+These are the new-engine analogue of the reference's engine-vs-engine suite tests/test_shtns_backend.py."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, field_norm_err, load_group
+from oracle import oracle as O
+import shxarray_b200 as sb
+from shxarray_b200 import capi, synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12          # north_star: <= 1e-12 relative (field norm) in FP64
+FLAG_SETS = [0, capi.FLAG_NO_DMMA, capi.FLAG_NO_DMMA | capi.FLAG_NO_SYMMETRY, capi.FLAG_DENSE_LON]
+
+
+def per_field_err(a, ref):
+    """a, ref: [B, ...] -> max over fields of max|d|/max|ref|."""
+    B = a.shape[0]
+    a = a.reshape(B, -1)
+    ref = ref.reshape(B, -1)
+    return float(np.max(np.abs(a - ref).max(axis=1) / np.abs(ref).max(axis=1)))
+
+
+# ---------------------------------------------------------------------------------------------------
+def test_device_recursion_bit_exact():
+    """The DFMA-path recursion reproduces Legendre_nm<double>::set bit for bit (Legendre_nm.hpp:89-132)."""
+    for nmax, lats in ((20, [0.0, 33.3, -89.5]), (200, [0.25, -31.0, 65.0, 89.75]), (720, [0.125, 45.0, 89.96, -89.9375]), (2160, [89.9583333, 12.0])):
+        for lat in lats:
+            dev = capi.debug_legendre(nmax, lat)
+            ref = O.legendre(nmax, np.sin(lat * np.pi / 180.0), "port")
+            assert np.array_equal(dev, ref), (nmax, lat, np.abs(dev - ref).max())
+
+
+@pytest.mark.parametrize("flags", FLAG_SETS)
+def test_known_answers_unit_field(engine, flags):
+    """test_synthesis.py:24-29,45-50: unit coefficients nmax=200/20 vs rlftlbx values, grid and point mode, 1e-7 rel."""
+    ka = json.load(open(os.path.join(GOLDEN, "ref_known_answers.json")))
+    for nmax, key in ((200, "nmax200"), (20, "nmax20")):
+        v = np.array(ka[key])
+        n, m = sb.nm_index(nmax)
+        out = engine.synthesis(np.ones((1, len(n))), n, m, v[:, 0], v[:, 1], points=True, flags=flags)[0]
+        assert np.abs((out - v[:, 2]) / v[:, 2]).max() < 1e-7
+        lon = np.arange(-180, 180.01, 60.0)
+        lat = np.arange(-60, 60.01, 60.0)
+        g = engine.synthesis(np.ones((1, len(n))), n, m, lon, lat, flags=flags)[0]
+        for lo, la, val in v:
+            got = g[np.where(lat == la)[0][0], np.where(lon == lo)[0][0]]
+            assert abs((got - val) / val) < 1e-7
+
+
+@pytest.mark.parametrize("nm_first", [False, True])
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_synthesis_layouts_and_truncation(engine, nm_first, order):
+    """fixtures.py:86-108 / test_synthesis.py:24-69: (basins,time) aux dims, C/F order, transposed, sliced views, nmin=1."""
+    nmax = 200
+    n, m = sb.nm_index(nmax)
+    scales = np.outer(np.arange(5), 0.3 * np.arange(4))            # basins x time
+    full = np.ones((5, 4, len(n))) * scales[:, :, None]
+    lon = np.arange(-180, 180.01, 60.0)
+    lat = np.arange(-60, 60.01, 60.0)
+    ref = O.synthesis(np.ones((1, len(n))), n, m, lon, lat, kind="port")[:, :, 0]
+    for sl_b, sl_t in ((slice(None), slice(None)), (slice(1, 4), slice(1, 3))):       # test_synthesis_slice
+        sub = full[sl_b, sl_t]
+        B = sub.shape[0] * sub.shape[1]
+        c2 = sub.reshape(B, len(n))
+        if nm_first:
+            arr = np.array(c2.T, order=order)       # [nsh, B]
+            out = engine.synthesis(arr, n, m, lon, lat, nm_axis=0)
+        else:
+            arr = np.array(c2, order=order)
+            out = engine.synthesis(arr, n, m, lon, lat)
+        sc = scales[sl_b, sl_t].reshape(-1)
+        assert np.abs(out - ref[None] * sc[:, None, None]).max() <= TOL * np.abs(ref).max() * max(sc.max(), 1)
+    # nmin=1 truncation (test_synthesis.py:32-42): Y00 = 1 everywhere
+    keep = n >= 1
+    out = engine.synthesis(np.ones((1, keep.sum())), n[keep], m[keep], lon, lat)[0]
+    assert np.abs(out - (ref - 1.0)).max() <= TOL * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("flags", FLAG_SETS)
+@pytest.mark.parametrize("tag", ["n60_regular", "n96_lon0", "n256_regular"])
+def test_synthesis_goldens_shlib_grids(engine, tag, flags):
+    if tag == "n256_regular" and flags == capi.FLAG_DENSE_LON:
+        pytest.skip("dense longitude stage is exercised on the smaller grids")
+    g = load_group(np.load(os.path.join(GOLDEN, "synthesis_shlib_grids.npz")), tag)
+    nmax, B = int(g["nmax"]), int(g["B"])
+    c = np.concatenate([S.random_coefficients(nmax, B - B // 2, kaula=True), S.random_coefficients(nmax, B // 2, kaula=False, seed=S.SEED + 1)])
+    grid = sb.lonlat_grid(nmax, gtype=str(g["gtype"]))
+    out = engine.synthesis(c, lon=grid["lon"], lat=grid["lat"], nmax=nmax, flags=flags)      # [B, L, K]
+    sub = out[:, g["rows"]][:, :, g["cols"]]
+    ref = np.moveaxis(g["values"], 2, 0)
+    assert per_field_err(sub, ref) <= TOL
+    # shlib output layout [lat, lon, B] (synthesis.pyx:68-71) gives identical numbers
+    out2 = engine.synthesis(c, lon=grid["lon"], lat=grid["lat"], nmax=nmax, layout="shlib", flags=flags)
+    assert np.array_equal(np.moveaxis(out2, 2, 0), out)
+
+
+@pytest.mark.parametrize("flags", [0, capi.FLAG_NO_DMMA])
+def test_synthesis_golden_n720_gauss(engine, flags):
+    z = np.load(os.path.join(GOLDEN, "synthesis_n720_gauss.npz"))
+    nmax = int(z["nmax"])
+    c = np.concatenate([S.random_coefficients(nmax, 1, kaula=True), S.random_coefficients(nmax, 1, kaula=False, seed=S.SEED + 1)])
+    out = engine.synthesis(c, lon=z["lon"], lat=z["lat"], nmax=nmax, flags=flags)
+    sub = out[:, z["rows"]][:, :, z["cols"]]
+    assert per_field_err(sub, np.moveaxis(z["values"], 2, 0)) <= TOL
+
+
+def test_synthesis_golden_n2160(engine):
+    z = np.load(os.path.join(GOLDEN, "synthesis_n2160_5min.npz"))
+    nmax = int(z["nmax"])
+    c = np.concatenate([S.random_coefficients(nmax, 1, kaula=True), S.random_coefficients(nmax, 1, kaula=False, seed=S.SEED + 1)])
+    out = engine.synthesis(c, lon=z["lon"], lat=z["lat"], nmax=nmax)
+    sub = out[:, z["rows"]][:, :, z["cols"]]
+    ref = np.moveaxis(z["values"], 2, 0)
+    # per-row normalisation would be stricter than the contract; the field max is the contract
+    fmax = np.abs(out).reshape(2, -1).max(axis=1)
+    err = np.abs(sub - ref).reshape(2, -1).max(axis=1) / fmax
+    assert err.max() <= TOL, err
+
+
+@pytest.mark.parametrize("flags", [0, capi.FLAG_NO_DMMA])
+def test_synthesis_points_subset_shuffled_duplicate(engine, flags):
+    """Ynm.hpp:84-101 accepts any (n,m) list: nmin=3, shuffled, one duplicated entry, poles included."""
+    z = np.load(os.path.join(GOLDEN, "synthesis_points_n120.npz"))
+    out = engine.synthesis(z["coef"], z["n"], z["m"], z["lon"], z["lat"], points=True, flags=flags)    # [B, npts]
+    assert per_field_err(out, z["values"].T) <= TOL
+    out2 = engine.synthesis(z["coef"], z["n"], z["m"], z["lon"], z["lat"], points=True, layout="shlib", flags=flags)
+    assert np.array_equal(out2.T, out)
+
+
+@pytest.mark.parametrize("flags", FLAG_SETS)
+@pytest.mark.parametrize("tag", ["n60_regular", "n48_lon0"])
+def test_analysis_goldens(engine, tag, flags):
+    g = load_group(np.load(os.path.join(GOLDEN, "analysis_shlib_grids.npz")), tag)
+    nmax, B = int(g["nmax"]), int(g["B"])
+    grid = sb.lonlat_grid(nmax, gtype=str(g["gtype"]))
+    f = np.random.default_rng(int(g["seed"])).standard_normal((B, len(grid["lat"]), len(grid["lon"])))
+    out = engine.analysis(f, nmax, grid["lon"], grid["lat"], quadrature="shlib", flags=flags)
+    assert out.shape == (B, (nmax + 1) ** 2)
+    assert per_field_err(out, g["values"]) <= TOL
+
+
+@pytest.mark.parametrize("layout", ["CN", "CT", "FN", "FT"])
+def test_analysis_paracap_known_answer(engine, layout):
+    """tests/test_analysis.py:14-25 with the four memory layouts of fixtures.py:41-54; tol 1e-7 absolute,
+    and 1e-12 field-norm against the oracle at nmax=200."""
+    z = np.load(os.path.join(GOLDEN, "paracap_n200.npz"))
+    f = z["z"]                                  # [time=2, y=360, x=720]
+    if layout[1] == "T":
+        arr = f.transpose(2, 1, 0)              # [x, y, time]
+        arr = np.array(arr, order=layout[0])
+        view = arr.transpose(2, 1, 0)           # back to [B, lat, lon] as a strided view
+    else:
+        view = np.array(f, order=layout[0])
+    out = engine.analysis(view, 200, z["x"], z["y"], quadrature="shlib")
+    assert np.abs(out - z["cap_coef"]).max() < 1e-7
+    if layout == "CN":
+        ref = O.analysis(f, 200, z["x"], z["y"], kind=O.best_kind())
+        assert per_field_err(out, ref) <= TOL
+
+
+def test_analysis_output_index_layout(engine):
+    """A grid equal to a single harmonic must land at position n^2+n+m (sh_indexing.py:66) and nowhere else."""
+    nmax = 12
+    grid = sb.lonlat_grid(nmax, gtype="gauss")
+    n, m = sb.nm_index(nmax)
+    picks = [(0, 0), (5, -3), (5, 3), (12, 12), (12, -12), (7, 0)]
+    coef = np.zeros((len(picks), len(n)))
+    for i, (a, b) in enumerate(picks):
+        coef[i, a * a + a + b] = 1.0
+    f = engine.synthesis(coef, lon=grid["lon"], lat=grid["lat"], nmax=nmax)
+    back = engine.analysis(f, nmax, grid["lon"], grid["lat"], quadrature="gauss")
+    assert np.abs(back - coef).max() < 1e-13
+
+
+# ---------------------------------------------------------------------------------------------------
+# properties at BASELINE sizes (no oracle needed)
+@pytest.mark.parametrize("nmax,B", [(96, 5), (256, 3), (720, 4)])
+def test_roundtrip_gauss_grid(engine, nmax, B):
+    """synthesis -> analysis with Gauss-Legendre weights recovers the coefficients (exact quadrature)."""
+    grid = sb.lonlat_grid(nmax, gtype="gauss")
+    c = S.random_coefficients(nmax, B, kaula=False)
+    f = engine.synthesis(c, lon=grid["lon"], lat=grid["lat"], nmax=nmax)
+    back = engine.analysis(f, nmax, grid["lon"], grid["lat"], quadrature="gauss")
+    assert per_field_err(back, c) < 5e-12
+
+
+def test_linearity_and_batch_independence(engine):
+    nmax, B = 256, 6
+    grid = sb.lonlat_grid(nmax, gtype="regular")
+    c = S.random_coefficients(nmax, B, kaula=True)
+    f = engine.synthesis(c, lon=grid["lon"], lat=grid["lat"], nmax=nmax)
+    f1 = engine.synthesis(c[2:3], lon=grid["lon"], lat=grid["lat"], nmax=nmax)
+    assert np.array_equal(f1[0], f[2])                      # a field does not depend on its batch neighbours
+    comb = 2.0 * c[0] - 0.5 * c[1]
+    fc = engine.synthesis(comb[None], lon=grid["lon"], lat=grid["lat"], nmax=nmax)[0]
+    assert np.abs(fc - (2.0 * f[0] - 0.5 * f[1])).max() <= 1e-13 * np.abs(fc).max()
+
+
+def test_adjointness_analysis_is_weighted_transpose(engine):
+    """<analysis(f), c> == sum_ij w_i f_ij synthesis(c)_ij: ties analysis parity to synthesis parity at any size."""
+    nmax = 360
+    grid = sb.lonlat_grid(nmax, gtype="regular_lon0")
+    lon, lat = grid["lon"], grid["lat"]
+    rng = np.random.default_rng(5)
+    f = rng.standard_normal((2, len(lat), len(lon)))
+    c = S.random_coefficients(nmax, 2, kaula=False, seed=11)
+    a = engine.analysis(f, nmax, lon, lat, quadrature="shlib")
+    s = engine.synthesis(c, lon=lon, lat=lat, nmax=nmax)
+    w = sb.analysis_weight_shlib(lon, lat) * np.cos(lat * (np.pi / 180))
+    lhs = np.einsum("bk,bk->b", a, c)
+    rhs = np.einsum("bij,bij,i->b", f, s, w)
+    assert np.abs(lhs - rhs).max() <= 1e-12 * np.abs(rhs).max()
+
+
+def test_device_tensor_path_matches_host_path(engine):
+    import torch
+    nmax, B = 96, 7
+    grid = sb.lonlat_grid(nmax, gtype="regular")
+    c = S.random_coefficients(nmax, B, kaula=True)
+    fh = engine.synthesis(c, lon=grid["lon"], lat=grid["lat"], nmax=nmax)
+    ct = torch.from_numpy(c).cuda()
+    ft = engine.synthesis(ct, lon=grid["lon"], lat=grid["lat"], nmax=nmax)
+    assert ft.is_cuda and np.array_equal(ft.cpu().numpy(), fh)
+    ah = engine.analysis(fh, nmax, grid["lon"], grid["lat"])
+    at = engine.analysis(ft, nmax, grid["lon"], grid["lat"])
+    assert np.array_equal(at.cpu().numpy(), ah)
+
+
+def test_edge_cases(engine):
+    # nmax = 0, single latitude, single field; odd sizes; batch not a multiple of the column block
+    out = engine.synthesis(np.array([[2.5]]), np.array([0]), np.array([0]), [10.0, 20.0, 30.0], [5.0])
+    assert np.allclose(out, 2.5, rtol=0, atol=1e-15)
+    nmax = 7
+    n, m = sb.nm_index(nmax)
+    c = S.random_coefficients(nmax, 3, kaula=False)
+    lon = np.array([0.0, 13.0, 200.5, -77.0, 359.0])
+    lat = np.array([-90.0, -12.5, 0.0, 12.5, 90.0, 44.0])
+    ref = O.synthesis(c, n, m, lon, lat, kind="port")
+    out = engine.synthesis(c, n, m, lon, lat)
+    assert per_field_err(out, np.moveaxis(ref, 2, 0)) <= TOL
+    with pytest.raises(ValueError):
+        engine.synthesis(c[:, :-1], n, m, lon, lat)
+    with pytest.raises(RuntimeError):      # analysis.pyx:39-40: non-equidistant grid is rejected for shlib quadrature
+        engine.analysis(np.zeros((1, 6, 5)), 3, lon, lat, quadrature="shlib")
