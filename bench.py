@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric: SH synthesis+analysis fields/s (FP64) at nmax=720, batch 64, on N B200s.
+
+One step = one pass of the hot path over one batch: 64 random Stokes fields synthesised to the
+724 x 1536 Gauss grid AND analysed back (a "field" = one round trip).  Multi-GPU = batch sharding
+(SURVEY.md §8e.1): every rank owns its own 64 fields, no data-path collective, weak scaling.
+
+  value    : device-resident round trips/s (inputs already in HBM), whole job, max-over-ranks time
+  e2e      : the same through the host-buffer C-ABI call the plugin makes (pinned host numpy in/out,
+             H2D + D2H inside the timed region)
+  roofline : dominant kernel (Legendre stage, FP64 tensor pipe), algorithmic flops / CUDA-event time
+  cpu_baseline : the shlib arithmetic (oracle/_ref, else the C port) on the host cores, bounded sample
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NMAX, NLAT, NLON, BATCH = 720, 724, 1536, 64
+METRIC = "SH synthesis+analysis fields/sec (FP64) at nmax=720 batch 64"
+UNIT = "fields/s"
+
+
+def workload_config(ngpu):
+    return {"workload": f"cfg3: nmax={NMAX} Gauss grid {NLAT}x{NLON}, batch {BATCH} per GPU, synthesis+analysis round trip",
+            "nmax": NMAX, "grid": [NLAT, NLON], "batch_per_gpu": BATCH, "parallelism": f"batch-shard x{ngpu} (no collective)",
+            "l2": "inputs larger than L2 (coefficients 266 MB + grid 570 MB per step)"}
+
+
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smmax, reasons = [], None, set()
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                try:
+                    sm.append(float(f[1]))
+                    smmax = float(f[2])
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smmax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def fp64_peak_tflops():
+    """Measured FP64 tensor-pipe (DMMA m8n8k4) peak on this pool's B200 (tools/fp64_peaks.cu -> profiles/)."""
+    path = os.path.join(ROOT, "profiles", "fp64_peaks_r01.json")
+    try:
+        d = json.load(open(path))
+        return float(d["dmma884_tflops_occ8"]), "measured FP64 DMMA peak, profiles/fp64_peaks_r01.json (MEASURED_PEAKS.json has no FP64 entry)"
+    except Exception:
+        return 37.2, "fallback: nominal 148 SM x 64 FMA/clk x 1.965 GHz"
+
+
+# --------------------------------------------------------------------------------------------------
+def cpu_sample(steps, warmup, per_step_scale=1.0):
+    """Time the shlib arithmetic on a bounded sample of cfg3 and extrapolate linearly in the number of grid
+    points (every point costs the same in synthesis.pyx:179-183 / analysis.pyx:128-139)."""
+    from oracle import oracle as O
+    from shxarray_b200 import synthetic as S
+    kind = O.best_kind()
+    nthr = O.max_threads()
+    lon, lat, _ = S.gauss_grid(NLAT, NLON)
+    n, m = O.nm_index(NMAX)
+    c = S.random_coefficients(NMAX, BATCH, kaula=True)
+    rows = np.linspace(0, NLAT - 1, max(nthr, 2)).round().astype(int)       # >= 1 latitude row per thread (prange over rows)
+    nl_syn = max(2, int(round(16 * per_step_scale)))
+    nl_ana = max(1, int(round(96 * per_step_scale / len(rows))) or 1)
+    cols_s = np.linspace(0, NLON - 1, nl_syn).round().astype(int)
+    cols_a = np.linspace(0, NLON - 1, nl_ana).round().astype(int)
+    rng = np.random.default_rng(1)
+    f = rng.standard_normal((BATCH, len(rows), len(cols_a)))
+    w = 1.0 / (2.0 * NLON)
+    vals, t_syn, t_ana = [], [], []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.synthesis(c, n, m, lon[cols_s], lat[rows], grid=True, kind=kind)
+        t1 = time.perf_counter()
+        O.analysis(f, NMAX, lon[cols_a], lat[rows], kind=kind, weight=w)
+        t2 = time.perf_counter()
+        if it >= warmup:
+            full_s = (t1 - t0) * (NLAT * NLON) / (len(rows) * len(cols_s))
+            full_a = (t2 - t1) * (NLAT * NLON) / (len(rows) * len(cols_a))
+            t_syn.append(full_s)
+            t_ana.append(full_a)
+            vals.append(BATCH / (full_s + full_a))
+    sample = (f"shlib loops ({'reference headers + scipy OpenBLAS' if kind == 'ref' else 'C port'}) on {len(rows)} of {NLAT} latitude rows x "
+              f"{len(cols_s)} (synthesis) / {len(cols_a)} (analysis) of {NLON} longitudes, batch {BATCH}, extrapolated linearly in grid points")
+    return dict(value=float(np.mean(vals)), unit=UNIT, cores=int(nthr), kind="reference" if kind == "ref" else "port", sample=sample,
+                synthesis_s_per_batch=float(np.mean(t_syn)), analysis_s_per_batch=float(np.mean(t_ana))), float(np.mean(t_syn) + np.mean(t_ana))
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    base, tstep = cpu_sample(args.steps, args.warmup, per_step_scale=0.5)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": tstep * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus), "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--flags", type=int, default=0, help="extra SHB200_FLAG_* bits (e.g. 4 = force DFMA kernels)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from shxarray_b200 import capi, synthetic as S
+    import shxarray_b200 as sb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    # ---- plans and inputs (device resident) ------------------------------------------------------
+    grid = sb.lonlat_grid(NMAX, gtype="gauss")
+    lon, lat, latw = grid["lon"], grid["lat"], grid["lat_weights"]
+    assert len(lat) == NLAT and len(lon) == NLON
+    flags = capi.FLAG_TIMING | args.flags
+    plan = capi.Plan(NMAX, lat, lon, max_batch=BATCH, quadrature=capi.QUAD_LATWEIGHTS, weight=1.0 / (2.0 * NLON), lat_weights=latw, flags=flags, device=local)
+    nsh = plan.nsh_full
+    coef_h = torch.from_numpy(S.random_coefficients(NMAX, BATCH, kaula=True, seed=S.SEED + rank)).pin_memory()
+    coef = coef_h.cuda()
+    gridbuf = torch.empty((BATCH, NLAT, NLON), dtype=torch.float64, device="cuda")
+    coef_out = torch.empty((BATCH, nsh), dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        plan.synthesis_dev(BATCH, coef.data_ptr(), nsh, 1, gridbuf.data_ptr(), NLAT * NLON, NLON, 1, stream)
+        plan.analysis_dev(BATCH, gridbuf.data_ptr(), NLAT * NLON, NLON, 1, coef_out.data_ptr(), nsh, 1, stream)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    rt_err = float(((coef_out - coef).abs().amax(dim=1) / coef.abs().amax(dim=1)).max().item())
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize()
+    t_wall0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    value = world * BATCH * args.steps / (ms_total * 1e-3)
+
+    # ---- per-kernel durations (CUDA events recorded by the library on the launching stream) -----
+    acc = {}
+    for _ in range(args.steps):
+        step()
+        st = plan.stage_times()
+        for k, v in st.items():
+            acc[k] = acc.get(k, 0.0) + v / args.steps
+    L_rows = plan.info.nrows
+    paired = L_rows < NLAT
+    flops_leg = (1.0 if paired else 2.0) * nsh * NLAT * BATCH          # F_sym / F_alg Legendre term x batch
+    dom = "syn_legendre" if acc["syn_legendre"] >= acc["ana_legendre"] else "ana_legendre"
+    peak, peak_src = fp64_peak_tflops()
+    achieved = flops_leg / (acc[dom] * 1e-3) * 1e-12
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "flops_per_launch": flops_leg, "ms_per_launch": acc[dom], "peak_source": peak_src,
+                "symmetry": "mirror-latitude pairing used: F_sym = nsh*L per field" if paired else "no pairing: F_alg = 2*nsh*L per field",
+                "stages_ms": acc}
+
+    # ---- end to end through the host-buffer C-ABI calls (pinned numpy in / out) ------------------
+    grid_h = torch.empty((BATCH, NLAT, NLON), dtype=torch.float64).pin_memory()
+    out_h = torch.empty((BATCH, nsh), dtype=torch.float64).pin_memory()
+    cnp, gnp, onp = coef_h.numpy(), grid_h.numpy(), out_h.numpy()
+
+    def step_e2e():
+        plan.synthesis_host(BATCH, cnp.ctypes.data, nsh, 1, gnp.ctypes.data, NLAT * NLON, NLON, 1)
+        plan.analysis_host(BATCH, gnp.ctypes.data, NLAT * NLON, NLON, 1, onp.ctypes.data, nsh, 1)
+
+    step_e2e()
+    ke = max(3, min(args.steps, 10))
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(ke):
+        step_e2e()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_val = world * BATCH * ke / float(dt.item())
+    nb_c, nb_g = BATCH * nsh * 8, BATCH * NLAT * NLON * 8
+    e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": nb_c + nb_g, "d2h_bytes_per_step": nb_c + nb_g, "steps": ke,
+           "roundtrip_max_rel_err": float((np.abs(onp - cnp).max(axis=1) / np.abs(cnp).max(axis=1)).max())}
+
+    launches = args.steps * (plan.info.launches_synthesis + plan.info.launches_analysis)
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": workload_config(world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+                "roofline": roofline, "roundtrip_max_rel_err": rt_err,
+                "dmma": bool(plan.info.dmma), "lon_fft": bool(plan.info.lon_fft)}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"], _ = cpu_sample(1, 0)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -41,7 +41,8 @@ enum { SHB200_QUAD_NONE = 0,      /* plan is synthesis-only */
 /* shb200_plan_desc.flags */
 enum { SHB200_FLAG_NO_SYMMETRY = 1, /* do not pair mirror latitudes */
        SHB200_FLAG_DENSE_LON = 2,   /* force the dense trig longitude stage (no FFT) */
-       SHB200_FLAG_NO_DMMA = 4      /* force the CUDA-core (DFMA) Legendre kernels */ };
+       SHB200_FLAG_NO_DMMA = 4,     /* force the CUDA-core (DFMA) Legendre kernels */
+       SHB200_FLAG_TIMING = 8       /* record CUDA events around every stage (see shb200_plan_stage_times) */ };
 
 typedef struct shb200_plan shb200_plan;
 
@@ -83,6 +84,11 @@ const char* shb200_last_error(void);
 int shb200_plan_create(const shb200_plan_desc* desc, shb200_plan** out);
 void shb200_plan_destroy(shb200_plan* plan);
 int shb200_plan_get_info(const shb200_plan* plan, shb200_plan_info* info);
+
+/* Per-stage device times (ms) of the most recent synthesis (ms[0..2] = pack, legendre, longitude) and analysis
+ * (ms[3..5] = longitude, legendre, unpack) call on a plan created with SHB200_FLAG_TIMING.  CUDA events recorded on
+ * the launching stream; the call synchronises that stream's last event.  Used by bench.py for the roofline. */
+int shb200_plan_stage_times(shb200_plan* plan, double* ms, int32_t n);
 
 /* Synthesis  f(b, point) = sum_k C(b,k) * Ybar_{n_k m_k}(point)      [synthesis.pyx:175-189]
  *   coef element (b,k)          at coef[b*cs_b + k*cs_nm]             (device pointer, element strides)

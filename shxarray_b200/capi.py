@@ -15,13 +15,13 @@ LIB_PATH = os.path.join(_HERE, "libshb200.so")
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
 MODE_GRID, MODE_POINTS = 0, 1
 QUAD_NONE, QUAD_SHLIB, QUAD_LATWEIGHTS = 0, 1, 2
-FLAG_NO_SYMMETRY, FLAG_DENSE_LON, FLAG_NO_DMMA = 1, 2, 4
+FLAG_NO_SYMMETRY, FLAG_DENSE_LON, FLAG_NO_DMMA, FLAG_TIMING = 1, 2, 4, 8
 
 # every symbol declared in include/shb200.h
 EXPORTS = [
     "shb200_version", "shb200_last_error", "shb200_plan_create", "shb200_plan_destroy", "shb200_plan_get_info",
     "shb200_synthesis", "shb200_analysis", "shb200_synthesis_host", "shb200_analysis_host", "shb200_multiply",
-    "shb200_gauss_nodes", "shb200_debug_legendre",
+    "shb200_gauss_nodes", "shb200_debug_legendre", "shb200_plan_stage_times",
 ]
 
 
@@ -73,6 +73,7 @@ def lib():
     L.shb200_synthesis_host.argtypes = [vp, i32, vp, i64, i64, vp, i64, i64, i64]
     L.shb200_analysis_host.argtypes = [vp, i32, vp, i64, i64, i64, vp, i64, i64]
     L.shb200_multiply.argtypes = [vp, vp, vp, i32, vp, i64, i64, vp, i64, i64, vp, i64, i64, vp]
+    L.shb200_plan_stage_times.argtypes = [vp, vp, i32]
     L.shb200_gauss_nodes.argtypes = [i32, vp, vp]
     L.shb200_debug_legendre.argtypes = [i32, i32, dbl, vp]
     for name in EXPORTS:
@@ -175,6 +176,12 @@ class Plan:
             self.close()
         except Exception:
             pass
+
+    def stage_times(self):
+        """dict of per-stage device ms of the last synthesis/analysis (plan needs FLAG_TIMING)."""
+        ms = np.zeros(6)
+        check(lib().shb200_plan_stage_times(self._h, ms.ctypes.data, 6))
+        return dict(syn_pack=ms[0], syn_legendre=ms[1], syn_lon=ms[2], ana_lon=ms[3], ana_legendre=ms[4], ana_unpack=ms[5])
 
     # raw calls: pointers are integers (device or host addresses), strides in elements
     def synthesis_dev(self, batch, coef_ptr, cs_b, cs_nm, grid_ptr, gs_b, gs_lat, gs_lon, stream=0):

@@ -87,6 +87,8 @@ struct Plan {
     double* stage_grid = nullptr; int64_t stage_grid_elems = 0;
     cudaStream_t own_stream = nullptr;
     int launches_syn = 0, launches_ana = 0;
+    cudaEvent_t ev[8] = {};     // SHB200_FLAG_TIMING: syn 0..3, ana 4..7
+    bool timed_syn = false, timed_ana = false;
 };
 
 }  // namespace shb

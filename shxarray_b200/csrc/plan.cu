@@ -254,6 +254,8 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
     SHB_CUDA(cudaMemset(p.Cm, 0, sizeof(double) * (size_t)T * p.NC));
     SHB_CUDA(cudaMemset(p.G, 0, sizeof(double) * (size_t)(N + 1) * R * 2 * p.NC));
     SHB_CUDA(cudaStreamCreateWithFlags(&p.own_stream, cudaStreamNonBlocking));
+    if (d.flags & SHB200_FLAG_TIMING)
+        for (int i = 0; i < 8; ++i) SHB_CUDA(cudaEventCreate(&p.ev[i]));
     p.launches_syn = 3 + (p.ndup ? 1 : 0);
     p.launches_ana = 3;
     return 0;
@@ -266,6 +268,7 @@ static void free_plan(Plan& p) {
     if (p.stage_coef) cudaFree(p.stage_coef);
     if (p.stage_grid) cudaFree(p.stage_grid);
     if (p.own_stream) cudaStreamDestroy(p.own_stream);
+    for (int i = 0; i < 8; ++i) if (p.ev[i]) cudaEventDestroy(p.ev[i]);
 }
 
 static int check_batch(const Plan& p, int batch) {
@@ -320,10 +323,15 @@ int shb200_synthesis(shb200_plan* plan, int32_t batch, const double* coef, int64
     if (rc) return rc;
     SHB_CUDA(cudaSetDevice(p.device));
     cudaStream_t st = (cudaStream_t)stream;
+    const bool tm = p.flags & SHB200_FLAG_TIMING;
+    if (tm) cudaEventRecord(p.ev[0], st);
     launch_pack(p, batch, coef, cs_b, cs_nm, st);
+    if (tm) cudaEventRecord(p.ev[1], st);
     launch_legendre_syn(p, st);
+    if (tm) cudaEventRecord(p.ev[2], st);
     rc = launch_lon_syn(p, batch, grid, gs_b, gs_lat, gs_lon, st);
     if (rc) return rc;
+    if (tm) { cudaEventRecord(p.ev[3], st); p.timed_syn = true; }
     SHB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -337,11 +345,34 @@ int shb200_analysis(shb200_plan* plan, int32_t batch, const double* grid, int64_
     if (rc) return rc;
     SHB_CUDA(cudaSetDevice(p.device));
     cudaStream_t st = (cudaStream_t)stream;
+    const bool tm = p.flags & SHB200_FLAG_TIMING;
+    if (tm) cudaEventRecord(p.ev[4], st);
     rc = launch_lon_ana(p, batch, grid, gs_b, gs_lat, gs_lon, st);
     if (rc) return rc;
+    if (tm) cudaEventRecord(p.ev[5], st);
     launch_legendre_ana(p, st);
+    if (tm) cudaEventRecord(p.ev[6], st);
     launch_unpack(p, batch, coef, cs_b, cs_nm, st);
+    if (tm) { cudaEventRecord(p.ev[7], st); p.timed_ana = true; }
     SHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int shb200_plan_stage_times(shb200_plan* plan, double* ms, int32_t n) {
+    if (!plan || !ms || n < 6) { set_error("plan_stage_times: need a plan and room for 6 values"); return SHB200_EINVAL; }
+    Plan& p = plan->p;
+    if (!(p.flags & SHB200_FLAG_TIMING)) { set_error("plan_stage_times: plan was created without SHB200_FLAG_TIMING"); return SHB200_EINVAL; }
+    SHB_CUDA(cudaSetDevice(p.device));
+    for (int i = 0; i < 6; ++i) ms[i] = 0.0;
+    float f;
+    if (p.timed_syn) {
+        SHB_CUDA(cudaEventSynchronize(p.ev[3]));
+        for (int i = 0; i < 3; ++i) { SHB_CUDA(cudaEventElapsedTime(&f, p.ev[i], p.ev[i + 1])); ms[i] = f; }
+    }
+    if (p.timed_ana) {
+        SHB_CUDA(cudaEventSynchronize(p.ev[7]));
+        for (int i = 0; i < 3; ++i) { SHB_CUDA(cudaEventElapsedTime(&f, p.ev[4 + i], p.ev[5 + i])); ms[3 + i] = f; }
+    }
     return 0;
 }
 
