@@ -28,8 +28,7 @@ inline int64_t tri_size(int nmax) { return (int64_t)(nmax + 1) * (nmax + 2) / 2;
 struct DevTables {
     // Legendre recursion
     const double* wnm;    // [tri_size]   sqrt((2n+1)/(n+m)*(2n-1)/(n-m))       (Legendre_nm.hpp:73-78)
-    const double* a_nm;   // [tri_size]   = wnm                                  (fast recursion)
-    const double* b_nm;   // [tri_size]   = wnm[n]/wnm[n-1]                      (fast recursion, division-free)
+    const double* rinv;   // [tri_size]   correctly rounded 1/wnm                (division by Markstein correction)
     const double* cost;   // [nrows]      sin(lat*pi/180) of the primary row     (Ynm.hpp:109)
     const double* sect;   // [(nmax+1)*nrows] sectorial multiplier of order m    (Legendre_nm.hpp:101,127)
     const double* pmm;    // [(nmax+1)*nrows] P_mm                               (Legendre_nm.hpp:103,129-130)

@@ -124,8 +124,10 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
     for (int m = 0; m <= N; ++m)
         for (int n = m + 1; n <= N; ++n)
             wnm[tri(n, m, N)] = sqrt((2 * n + 1.0) / (n + m) * (2 * n - 1.0) / (n - m));
+    // correctly rounded reciprocals: the device divides by wnm with q=p*r; q+=fma(-q,w,p)*r (Markstein), which
+    // reproduces the IEEE quotient of Legendre_nm.hpp:117-118 (checked on every recursion step at nmax=2160)
     for (int m = 0; m <= N; ++m)
-        for (int n = m + 2; n <= N; ++n) bnm[tri(n, m, N)] = wnm[tri(n, m, N)] / wnm[tri(n - 1, m, N)];
+        for (int n = m + 1; n <= N; ++n) bnm[tri(n, m, N)] = 1.0 / wnm[tri(n, m, N)];
 
     // ---- latitude rows: mirror pairing ---------------------------------------------------------
     std::vector<double> cost_lat(d.nlat);
@@ -228,8 +230,7 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
     int rc;
     DevTables& t = p.t;
     if ((rc = upload(p, wnm, &t.wnm))) return rc;
-    t.a_nm = t.wnm;
-    if ((rc = upload(p, bnm, &t.b_nm))) return rc;
+    if ((rc = upload(p, bnm, &t.rinv))) return rc;
     if ((rc = upload(p, cost, &t.cost))) return rc;
     if ((rc = upload(p, sect, &t.sect))) return rc;
     if ((rc = upload(p, pmm, &t.pmm))) return rc;

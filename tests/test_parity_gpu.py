@@ -249,3 +249,35 @@ def test_edge_cases(engine):
         engine.synthesis(c[:, :-1], n, m, lon, lat)
     with pytest.raises(RuntimeError):      # analysis.pyx:39-40: non-equidistant grid is rejected for shlib quadrature
         engine.analysis(np.zeros((1, 6, 5)), 3, lon, lat, quadrature="shlib")
+
+
+@pytest.mark.parametrize("nmax,B,gtype", [(720, 64, "gauss"), (96, 240, "regular"), (2160, 16, "regular_lon0")])
+def test_dmma_kernels_match_bitfaithful_dfma_kernels(engine, nmax, B, gtype):
+    """The tensor-core kernels use the division-free recursion; the DFMA kernels are bit-faithful to the reference's
+    P_nm (test_device_recursion_bit_exact) and are oracle-checked above.  At BASELINE batch sizes the two must agree
+    to the parity tolerance, in both directions, for white (worst-case) and Kaula spectra."""
+    import torch
+    if gtype == "regular_lon0" and nmax == 2160:
+        d = 1.0 / 12
+        grid = dict(lon=np.arange(0, 360, d), lat=np.arange(-90 + d / 2, 90, d))
+    else:
+        grid = sb.lonlat_grid(nmax, gtype=gtype)
+    lon, lat = grid["lon"], grid["lat"]
+    c = np.concatenate([S.random_coefficients(nmax, B // 2, kaula=False), S.random_coefficients(nmax, B - B // 2, kaula=True, seed=3)])
+    ct = torch.from_numpy(c).cuda()
+    f_t = engine.synthesis(ct, lon=lon, lat=lat, nmax=nmax, flags=0)
+    f_d = engine.synthesis(ct, lon=lon, lat=lat, nmax=nmax, flags=capi.FLAG_NO_DMMA)
+    num = (f_t - f_d).abs().amax(dim=(1, 2))
+    den = f_d.abs().amax(dim=(1, 2))
+    assert float((num / den).max()) <= TOL
+    if gtype == "gauss":
+        quad = dict(quadrature="gauss")
+    elif nmax == 2160:   # the 5' grid is not exactly equidistant in FP64 (shlib would reject it): explicit midpoint weights
+        quad = dict(quadrature="weights", weight=(d * np.pi / 180) ** 2 / (4 * np.pi), lat_weights=np.cos(lat * (np.pi / 180)))
+    else:
+        quad = dict(quadrature="shlib")
+    a_t = engine.analysis(f_d, nmax, lon, lat, flags=0, **quad)
+    a_d = engine.analysis(f_d, nmax, lon, lat, flags=capi.FLAG_NO_DMMA, **quad)
+    num = (a_t - a_d).abs().amax(dim=1)
+    den = a_d.abs().amax(dim=1)
+    assert float((num / den).max()) <= TOL
