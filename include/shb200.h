@@ -42,7 +42,8 @@ enum { SHB200_QUAD_NONE = 0,      /* plan is synthesis-only */
 enum { SHB200_FLAG_NO_SYMMETRY = 1, /* do not pair mirror latitudes */
        SHB200_FLAG_DENSE_LON = 2,   /* force the dense trig longitude stage (no FFT) */
        SHB200_FLAG_NO_DMMA = 4,     /* force the CUDA-core (DFMA) Legendre kernels */
-       SHB200_FLAG_TIMING = 8       /* record CUDA events around every stage (see shb200_plan_stage_times) */ };
+       SHB200_FLAG_TIMING = 8,      /* record CUDA events around every stage (see shb200_plan_stage_times) */
+       SHB200_FLAG_NO_PTABLE = 16   /* never keep a device-resident P_nm table: fused on-the-fly recursion kernels */ };
 
 typedef struct shb200_plan shb200_plan;
 
@@ -63,14 +64,14 @@ typedef struct shb200_plan_desc {
     double weight;        /* quadrature prefactor, e.g. |dlon*dlat|/(4 pi) in radians (analysis.pyx:57-60) */
     const double* lat_weights; /* host, nlat entries, SHB200_QUAD_LATWEIGHTS only */
     int32_t flags;        /* SHB200_FLAG_* */
-    int32_t reserved;
+    int32_t ptable_budget_mib; /* largest P_nm table the plan may keep in HBM, MiB; 0 = default (6144) */
 } shb200_plan_desc;
 
 typedef struct shb200_plan_info {
     int32_t nmax, max_batch, padded_batch;
     int32_t nlat, nlon, nrows;   /* nrows = mirror-paired latitude rows actually iterated */
     int32_t lon_fft;             /* 1 = FFT longitude stage, 0 = dense trig sums */
-    int32_t dmma;                /* 1 = FP64 tensor-core Legendre kernels selected */
+    int32_t dmma;                /* 0 = CUDA-core kernels, 1 = tensor-core kernels with fused recursion, 2 = tensor-core kernels + P_nm table */
     int64_t nsh;                 /* length of the synthesis nm list */
     int64_t nsh_full;            /* (nmax+1)^2 = analysis output length */
     int64_t workspace_bytes;     /* device memory owned by the plan */

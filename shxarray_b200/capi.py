@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libshb200.so")
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
 MODE_GRID, MODE_POINTS = 0, 1
 QUAD_NONE, QUAD_SHLIB, QUAD_LATWEIGHTS = 0, 1, 2
-FLAG_NO_SYMMETRY, FLAG_DENSE_LON, FLAG_NO_DMMA, FLAG_TIMING = 1, 2, 4, 8
+FLAG_NO_SYMMETRY, FLAG_DENSE_LON, FLAG_NO_DMMA, FLAG_TIMING, FLAG_NO_PTABLE = 1, 2, 4, 8, 16
 
 # every symbol declared in include/shb200.h
 EXPORTS = [
@@ -31,7 +31,7 @@ class PlanDesc(C.Structure):
         ("nsh", C.c_int64), ("n", C.c_void_p), ("m", C.c_void_p),
         ("mode", C.c_int32), ("nlat", C.c_int32), ("lat_deg", C.c_void_p),
         ("nlon", C.c_int32), ("quadrature", C.c_int32), ("lon_deg", C.c_void_p),
-        ("weight", C.c_double), ("lat_weights", C.c_void_p), ("flags", C.c_int32), ("reserved", C.c_int32),
+        ("weight", C.c_double), ("lat_weights", C.c_void_p), ("flags", C.c_int32), ("ptable_budget_mib", C.c_int32),
     ]
 
 
@@ -110,7 +110,7 @@ class Plan:
     """Owner of one ``shb200_plan``.  Coordinates/index arrays are host numpy arrays."""
 
     def __init__(self, nmax, lat, lon, max_batch=1, n=None, m=None, mode=MODE_GRID, quadrature=QUAD_NONE,
-                 weight=0.0, lat_weights=None, flags=0, device=0):
+                 weight=0.0, lat_weights=None, flags=0, device=0, ptable_budget_mib=0):
         L = lib()
         self._h = C.c_void_p()
         self._keep = []
@@ -150,6 +150,7 @@ class Plan:
                 raise ValueError("lat_weights must have nlat entries")
             d.lat_weights = lw.ctypes.data
         d.flags = int(flags)
+        d.ptable_budget_mib = int(ptable_budget_mib)
         check(L.shb200_plan_create(C.byref(d), C.byref(self._h)))
         info = PlanInfo()
         check(L.shb200_plan_get_info(self._h, C.byref(info)))

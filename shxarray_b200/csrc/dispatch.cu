@@ -4,14 +4,18 @@
 namespace shb {
 void launch_legendre_syn_dfma(const Plan& p, cudaStream_t st);
 void launch_legendre_ana_dfma(const Plan& p, cudaStream_t st);
+bool launch_legendre_syn_tab(const Plan& p, cudaStream_t st);
+bool launch_legendre_ana_tab(const Plan& p, cudaStream_t st);
 bool launch_legendre_syn_dmma(const Plan& p, cudaStream_t st);
 bool launch_legendre_ana_dmma(const Plan& p, cudaStream_t st);
 
 void launch_legendre_syn(const Plan& p, cudaStream_t st) {
+    if (p.dmma && launch_legendre_syn_tab(p, st)) return;
     if (p.dmma && launch_legendre_syn_dmma(p, st)) return;
     launch_legendre_syn_dfma(p, st);
 }
 void launch_legendre_ana(const Plan& p, cudaStream_t st) {
+    if (p.dmma && launch_legendre_ana_tab(p, st)) return;
     if (p.dmma && launch_legendre_ana_dmma(p, st)) return;
     launch_legendre_ana_dfma(p, st);
 }

@@ -77,6 +77,8 @@ struct Plan {
     std::vector<void*> owned;
     double* Cm = nullptr;   // [tri_size][NC]
     double* G = nullptr;    // [(nmax+1)][nrows][2][NC]
+    double* Ptab = nullptr; // [tri_size][Rpad] device-resident P_nm table (legendre_tab.cu) or null
+    int Rpad = 0;
     // duplicates in the nm list (rare; Ynm.hpp accepts them, dgemv sums them)
     int64_t ndup = 0;
     const int64_t* dup_slot = nullptr;  // device [ndup] slot*2+cs

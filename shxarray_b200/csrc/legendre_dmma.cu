@@ -17,6 +17,7 @@
 // Shared-memory rows are padded (stride = 16 B mod 64 B) so every 8x4 / 4x8 fragment load is conflict-free.
 #include "internal.h"
 #include "recursion.cuh"
+#include "dmma_common.cuh"
 
 namespace shb {
 namespace dm {
@@ -34,36 +35,6 @@ struct __align__(16) Stage {
     double C[CH][CROW];
 };
 constexpr size_t SMEM_SYN = sizeof(Stage) * STAGES + 2 * STAGES * sizeof(uint64_t);
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
-                 "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-}
 
 __global__ void __launch_bounds__(NTHREADS, 1) k_leg_syn_dmma(DevTables t, const double* __restrict__ Cm, double* __restrict__ G) {
     extern __shared__ __align__(128) unsigned char smraw[];
@@ -180,7 +151,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_leg_syn_dmma(DevTables t, const
 }
 
 }  // namespace dm
-using dm::bulk_g2s; using dm::dmma; using dm::mbar_arrive; using dm::mbar_init; using dm::mbar_wait; using dm::smem_u32;
 
 // ------------------------------------------------------------------------------------------------
 // Analysis kernel (k_leg_ana_dmma), one CTA = (order m, 128 columns):

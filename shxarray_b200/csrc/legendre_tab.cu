@@ -1,0 +1,293 @@
+// Legendre stage with a device-resident P_nm table: pure FP64 tensor-core (DMMA) contractions.
+//
+// Why a table: on sm_100a the DMMA and DFMA instructions share one FP64 datapath per SM sub-partition
+// (profiles/fp64_peaks_r01.json: mixed DMMA+DFMA adds up to the same ~37 TFLOP/s).  A producer warp that runs
+// the bit-faithful recursion inside the contraction kernel (legendre_dmma.cu) pays a full DMMA slot of pipe
+// latency for almost every one of its 7 FP64 instructions per degree and cannot feed 8 consumer warps
+// (ncu r01: consumers wait ~40 % of their time on the "P tile full" barrier).  The normalised P_nm depend
+// only on (nmax, latitudes) -- not on the data -- so the planner generates them ONCE per plan with the same
+// bit-faithful device recursion (k_ptab_gen, one thread per (row, order)) and keeps them in HBM:
+//     Ptab[tri(n,m)][Rpad]   (row fastest, Rpad = rows rounded up to 64, zero padded)
+// 0.8 GB for nmax=720 on 724 latitudes (362 mirror pairs).  Each transform then streams the table once
+// (0.12 ms at HBM speed, overlapped with the contraction) and the kernels below are TMA-fed DMMA GEMMs:
+//   synthesis  G[m][row][E/O][col] = sum_n Ptab[n,m][row] * Cm[n,m][col]      CTA = (m, 64 rows, 128 cols)
+//   analysis   Cm[n,m][col] = sum_row Ptab[n,m][row] * G[m][row][par(n-m)][col] CTA = (m, 128 cols), 128-degree super-blocks
+// One TMA warp (elected lane issues cp.async.bulk row copies into padded shared-memory tiles, mbarrier
+// complete_tx) + 8 consumer warps (64 DMMA.8x8x4 per stage each), full/empty mbarrier ring.
+// Plans whose table would not fit the budget fall back to the fused on-the-fly kernels.
+#include "internal.h"
+#include "recursion.cuh"
+#include "dmma_common.cuh"
+
+namespace shb {
+
+// ------------------------------------------------------------------------------------------------
+// table generation: thread <-> (row, order); writes are coalesced over rows
+__global__ void __launch_bounds__(128) k_ptab_gen(DevTables t, double* __restrict__ Ptab, int Rpad) {
+    const int m = blockIdx.y;
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= Rpad) return;
+    const int N = t.nmax, R = t.nrows;
+    const int64_t tmm = tri(m, m, N);
+    double* out = Ptab + tmm * Rpad + row;
+    if (row >= R) {
+        for (int k = 0; k <= N - m; ++k) out[(int64_t)k * Rpad] = 0.0;
+        return;
+    }
+    LegExact rec;
+    rec.init(t.cost[row], t.sect[(int64_t)m * R + row], m);
+    const double pmm = t.pmm[(int64_t)m * R + row];
+    const double* __restrict__ w = t.wnm + tmm;
+    const double* __restrict__ ri = t.rinv + tmm;
+    for (int k = 0; k <= N - m; ++k) out[(int64_t)k * Rpad] = rec.next(w, ri, pmm);
+}
+
+void launch_ptab_gen(const Plan& p, cudaStream_t st) {
+    dim3 grid((p.Rpad + 127) / 128, p.nmax + 1);
+    k_ptab_gen<<<grid, 128, 0, st>>>(p.t, p.Ptab, p.Rpad);
+}
+
+// ------------------------------------------------------------------------------------------------
+namespace ts {
+constexpr int TR = 64, CH = 16, NCOLS = 128;
+constexpr int PROW = TR + 2, CROW = NCOLS + 2;
+constexpr int STAGES = 8;
+constexpr int NCONS = 256, NTHREADS = NCONS + 32;
+struct __align__(16) Stage {
+    double P[CH][PROW];
+    double C[CH][CROW];
+};
+constexpr size_t SMEM = sizeof(Stage) * STAGES + 2 * STAGES * sizeof(uint64_t);
+}  // namespace ts
+
+__global__ void __launch_bounds__(ts::NTHREADS, 1) k_leg_syn_tab(DevTables t, const double* __restrict__ Ptab, int Rpad, const double* __restrict__ Cm,
+                                                                  double* __restrict__ G) {
+    using namespace ts;
+    extern __shared__ __align__(128) unsigned char smraw[];
+    Stage* st = reinterpret_cast<Stage*>(smraw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smraw + sizeof(Stage) * STAGES);
+    uint64_t* empty = full + STAGES;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m = blockIdx.y, row0 = blockIdx.x * TR, col0 = blockIdx.z * NCOLS;
+    const int N = t.nmax, R = t.nrows, NC = t.NC;
+    const int ncols = min(NCOLS, NC - col0);
+    const int nchunks = (N - m + CH) / CH;
+    const int64_t tmm = tri(m, m, N);
+
+    for (int i = tid; i < (int)(sizeof(Stage) * STAGES / 8); i += NTHREADS) reinterpret_cast<double*>(smraw)[i] = 0.0;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCONS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    if (warp == NCONS / 32) {
+        // ------------------------------------------------------------------ TMA warp: lane j streams row j of every stage
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int s = ch % STAGES;
+            mbar_wait(&empty[s], ((ch / STAGES) & 1) ^ 1);
+            const int k0 = ch * CH;
+            const int valid = min(CH, N - m - k0 + 1);
+            if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)(valid * (ncols + TR) * 8));
+            __syncwarp();
+            if (lane < valid) {
+                bulk_g2s(&st[s].C[lane][0], Cm + (tmm + k0 + lane) * NC + col0, (uint32_t)(ncols * 8), &full[s]);
+                bulk_g2s(&st[s].P[lane][0], Ptab + (tmm + k0 + lane) * Rpad + row0, (uint32_t)(TR * 8), &full[s]);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ consumers
+        const int wr = warp >> 2, wc = warp & 3;
+        const int lr = lane >> 2, lk = lane & 3;
+        double acc[2][4][4][2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb) { acc[e][g][cb][0] = 0.0; acc[e][g][cb][1] = 0.0; }
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int s = ch % STAGES;
+            mbar_wait(&full[s], (ch / STAGES) & 1);
+            const Stage& S = st[s];
+            const int valid = min(CH, N - m - ch * CH + 1);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int j = 8 * ks + 2 * lk + e;
+                    double A[4], B[4];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) A[g] = j < valid ? S.P[j][32 * wr + 8 * g + lr] : 0.0;   // rows beyond nmax hold stale data
+#pragma unroll
+                    for (int cb = 0; cb < 4; ++cb) B[cb] = S.C[j][32 * wc + 8 * cb + lr];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+#pragma unroll
+                        for (int cb = 0; cb < 4; ++cb) dmma(acc[e][g][cb][0], acc[e][g][cb][1], A[g], B[cb]);
+                }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int row = row0 + 32 * wr + 8 * g + lr;
+            if (row >= R) continue;
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb) {
+                    const int col = col0 + 32 * wc + 8 * cb + 2 * lk;
+                    if (col < NC) *reinterpret_cast<double2*>(G + (((int64_t)m * R + row) * 2 + e) * NC + col) = make_double2(acc[e][g][cb][0], acc[e][g][cb][1]);
+                }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+namespace ta {
+constexpr int RT = 32, NS = 32, SB = 128, NCOLS = 128;
+constexpr int PROW = RT + 2, CROW = NCOLS + 2;
+constexpr int PSTAGES = 8;
+constexpr int NCONS = 256, NTHREADS = NCONS + 32;
+struct __align__(16) GTile { double g[RT][2][CROW]; };
+struct __align__(16) PTile { double p[NS][PROW]; };
+constexpr size_t SMEM = sizeof(GTile) * 2 + sizeof(PTile) * PSTAGES + sizeof(uint64_t) * (2 * PSTAGES + 4);
+}  // namespace ta
+
+__global__ void __launch_bounds__(ta::NTHREADS, 1) k_leg_ana_tab(DevTables t, const double* __restrict__ Ptab, int Rpad, const double* __restrict__ G,
+                                                                  double* __restrict__ Cm) {
+    using namespace ta;
+    extern __shared__ __align__(128) unsigned char smraw[];
+    GTile* gt = reinterpret_cast<GTile*>(smraw);
+    PTile* ptile = reinterpret_cast<PTile*>(smraw + sizeof(GTile) * 2);
+    uint64_t* pfull = reinterpret_cast<uint64_t*>(smraw + sizeof(GTile) * 2 + sizeof(PTile) * PSTAGES);
+    uint64_t* pempty = pfull + PSTAGES;
+    uint64_t* gfull = pempty + PSTAGES;
+    uint64_t* gempty = gfull + 2;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m = blockIdx.x, col0 = blockIdx.y * NCOLS;
+    const int N = t.nmax, R = t.nrows, NC = t.NC;
+    const int ncols = min(NCOLS, NC - col0);
+    const int nsb = (N - m + SB) / SB;
+    const int nrt = (R + RT - 1) / RT;
+    const int64_t tmm = tri(m, m, N);
+
+    for (int i = tid; i < (int)((sizeof(GTile) * 2 + sizeof(PTile) * PSTAGES) / 8); i += NTHREADS) reinterpret_cast<double*>(smraw)[i] = 0.0;
+    if (tid == 0) {
+        for (int s = 0; s < PSTAGES; ++s) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], NCONS / 32); }
+        for (int g = 0; g < 2; ++g) { mbar_init(&gfull[g], 1); mbar_init(&gempty[g], NCONS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    if (warp == NCONS / 32) {
+        // ------------------------------------------------------------------ TMA warp
+        for (int sb = 0; sb < nsb; ++sb) {
+            for (int rt = 0; rt < nrt; ++rt) {
+                const int it = sb * nrt + rt;
+                const int gb = it & 1;
+                const int nr = min(RT, R - rt * RT);
+                mbar_wait(&gempty[gb], ((it >> 1) & 1) ^ 1);
+                if (lane == 0) mbar_arrive_expect_tx(&gfull[gb], (uint32_t)(nr * 2 * ncols * 8));
+                __syncwarp();
+                if (lane < nr) {
+                    const double* src = G + (((int64_t)m * R + rt * RT + lane) * 2) * NC + col0;
+                    bulk_g2s(&gt[gb].g[lane][0][0], src, (uint32_t)(ncols * 8), &gfull[gb]);
+                    bulk_g2s(&gt[gb].g[lane][1][0], src + NC, (uint32_t)(ncols * 8), &gfull[gb]);
+                }
+                for (int inner = 0; inner < SB / NS; ++inner) {
+                    const int sidx = it * (SB / NS) + inner;
+                    const int s = sidx % PSTAGES;
+                    mbar_wait(&pempty[s], ((sidx / PSTAGES) & 1) ^ 1);
+                    const int k0 = sb * SB + inner * NS;
+                    const int valid = max(0, min(NS, N - m - k0 + 1));
+                    if (lane == 0) mbar_arrive_expect_tx(&pfull[s], (uint32_t)(valid * RT * 8));
+                    __syncwarp();
+                    if (lane < valid) bulk_g2s(&ptile[s].p[lane][0], Ptab + (tmm + k0 + lane) * Rpad + rt * RT, (uint32_t)(RT * 8), &pfull[s]);
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ consumers
+        const int e = warp & 1, cq = warp >> 1;
+        const int lr = lane >> 2, lk = lane & 3;
+        double acc[8][4][2];
+        for (int sb = 0; sb < nsb; ++sb) {
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb) { acc[nb][cb][0] = 0.0; acc[nb][cb][1] = 0.0; }
+            for (int rt = 0; rt < nrt; ++rt) {
+                const int it = sb * nrt + rt;
+                const int gb = it & 1;
+                mbar_wait(&gfull[gb], (it >> 1) & 1);
+                const GTile& GT = gt[gb];
+#pragma unroll
+                for (int inner = 0; inner < SB / NS; ++inner) {
+                    const int sidx = it * (SB / NS) + inner;
+                    const int s = sidx % PSTAGES;
+                    mbar_wait(&pfull[s], (sidx / PSTAGES) & 1);
+                    const PTile& PT = ptile[s];
+                    const int valid = N - m - (sb * SB + inner * NS) + 1;     // degrees of this stage that exist
+#pragma unroll
+                    for (int ks = 0; ks < RT / 4; ++ks) {
+                        double A[2], B[4];
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const int j = 16 * q + 2 * lr + e;
+                            A[q] = j < valid ? PT.p[j][4 * ks + lk] : 0.0;
+                        }
+#pragma unroll
+                        for (int cb = 0; cb < 4; ++cb) B[cb] = GT.g[4 * ks + lk][e][32 * cq + 8 * cb + lr];
+#pragma unroll
+                        for (int q = 0; q < 2; ++q)
+#pragma unroll
+                            for (int cb = 0; cb < 4; ++cb) dmma(acc[2 * inner + q][cb][0], acc[2 * inner + q][cb][1], A[q], B[cb]);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&pempty[s]);
+                }
+                if (lane == 0) mbar_arrive(&gempty[gb]);
+            }
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+                const int k = sb * SB + 16 * nb + 2 * lr + e;
+                if (k > N - m) continue;
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb) {
+                    const int col = col0 + 32 * cq + 8 * cb + 2 * lk;
+                    if (col < NC) *reinterpret_cast<double2*>(Cm + (tmm + k) * NC + col) = make_double2(acc[nb][cb][0], acc[nb][cb][1]);
+                }
+            }
+        }
+    }
+}
+
+bool launch_legendre_syn_tab(const Plan& p, cudaStream_t st) {
+    if (!p.Ptab || p.NC < 32) return false;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(k_leg_syn_tab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts::SMEM) != cudaSuccess) return false;
+        attr = true;
+    }
+    dim3 grid((p.nrows + ts::TR - 1) / ts::TR, p.nmax + 1, (p.NC + ts::NCOLS - 1) / ts::NCOLS);
+    k_leg_syn_tab<<<grid, ts::NTHREADS, ts::SMEM, st>>>(p.t, p.Ptab, p.Rpad, p.Cm, p.G);
+    return true;
+}
+
+bool launch_legendre_ana_tab(const Plan& p, cudaStream_t st) {
+    if (!p.Ptab || p.NC < 32) return false;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(k_leg_ana_tab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ta::SMEM) != cudaSuccess) return false;
+        attr = true;
+    }
+    dim3 grid(p.nmax + 1, (p.NC + ta::NCOLS - 1) / ta::NCOLS);
+    k_leg_ana_tab<<<grid, ta::NTHREADS, ta::SMEM, st>>>(p.t, p.Ptab, p.Rpad, p.G, p.Cm);
+    return true;
+}
+
+}  // namespace shb

@@ -47,6 +47,8 @@ static int dev_alloc(Plan& p, size_t bytes, void** out) {
     return 0;
 }
 
+void launch_ptab_gen(const Plan& p, cudaStream_t st);
+
 static bool factor235(int K, std::vector<int>& radices) {
     radices.clear();
     int k = K;
@@ -255,6 +257,18 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
     SHB_CUDA(cudaMemset(p.Cm, 0, sizeof(double) * (size_t)T * p.NC));
     SHB_CUDA(cudaMemset(p.G, 0, sizeof(double) * (size_t)(N + 1) * R * 2 * p.NC));
     SHB_CUDA(cudaStreamCreateWithFlags(&p.own_stream, cudaStreamNonBlocking));
+    // device-resident P_nm table for the tensor-core kernels (legendre_tab.cu) when it fits the budget
+    if (p.dmma && !(d.flags & SHB200_FLAG_NO_PTABLE) && p.NC >= 32 && d.mode == SHB200_MODE_GRID) {
+        p.Rpad = (R + 63) / 64 * 64;
+        const double budget_mib = d.ptable_budget_mib > 0 ? (double)d.ptable_budget_mib : 6144.0;
+        const double need_mib = (double)T * p.Rpad * 8.0 / (1024.0 * 1024.0);
+        if (need_mib <= budget_mib) {
+            if ((rc = dev_alloc(p, sizeof(double) * (size_t)T * p.Rpad, &ptr))) return rc;
+            p.Ptab = (double*)ptr;
+            launch_ptab_gen(p, 0);
+            SHB_CUDA(cudaDeviceSynchronize());
+        }
+    }
     if (d.flags & SHB200_FLAG_TIMING)
         for (int i = 0; i < 8; ++i) SHB_CUDA(cudaEventCreate(&p.ev[i]));
     p.launches_syn = 3 + (p.ndup ? 1 : 0);
@@ -309,7 +323,7 @@ int shb200_plan_get_info(const shb200_plan* plan, shb200_plan_info* info) {
     const Plan& p = plan->p;
     info->nmax = p.nmax; info->max_batch = p.maxB; info->padded_batch = p.Bp;
     info->nlat = p.nlat; info->nlon = p.nlon; info->nrows = p.nrows;
-    info->lon_fft = p.lon_fft ? 1 : 0; info->dmma = p.dmma ? 1 : 0;
+    info->lon_fft = p.lon_fft ? 1 : 0; info->dmma = p.dmma ? (p.Ptab ? 2 : 1) : 0;
     info->nsh = p.nsh; info->nsh_full = (int64_t)(p.nmax + 1) * (p.nmax + 1);
     info->workspace_bytes = p.workspace_bytes;
     info->launches_synthesis = p.launches_syn; info->launches_analysis = p.launches_ana;
