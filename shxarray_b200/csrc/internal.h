@@ -57,8 +57,8 @@ void launch_legendre_ana(const Plan& p, cudaStream_t st);   // G  -> Cm
 // longitude stage
 int launch_lon_syn(const Plan& p, int batch, double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, cudaStream_t st);
 int launch_lon_ana(const Plan& p, int batch, const double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, cudaStream_t st);
-int lon_fft_smem_bytes(int K, int ntrans);
-int lon_fft_pick_ntrans(int K, int Bp);
+bool lon_fft_supported(int K, int Bp);
+void lon_fft_perm(int K, int Bp, std::vector<int>& perm);
 
 struct Plan {
     int device = 0, nmax = 0, maxB = 0, Bp = 0, NC = 0;
@@ -69,8 +69,7 @@ struct Plan {
     bool lon_fft = false;
     bool dmma = false;
     int K = 0;
-    std::vector<int> radices;
-    int fft_ntrans = 1;
+    const int* fft_perm = nullptr;   // device [K] digit-reversal table of the in-place FFT
     int64_t workspace_bytes = 0;
     DevTables t{};
     // owned device memory

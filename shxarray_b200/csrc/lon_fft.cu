@@ -1,0 +1,316 @@
+// Longitude stage, FFT path: batched complex FFTs in shared memory, two real latitude rows per transform.
+//
+// What it replaces in the reference: the trig factors cos(m*lon), sin(|m|*lon) of Ynm_cpp::set
+// (Ynm.hpp:114,121-131) that shlib folds into its per-point dgemv / dger (synthesis.pyx:183, analysis.pyx:136).
+//
+// Periodic equispaced longitudes lon_j = lon0 + j*360/K:
+//   synthesis: rows i (primary) and i' (mirror) of one latitude pair are the real and imaginary part of ONE complex
+//   inverse FFT ("two-for-one"): the Hermitian spectra are assembled from G[m][row][E/O][cos/sin][b] (E+O -> primary,
+//   E-O -> mirror) with the phase twist e^{i m lon0}; orders m >= K/2 alias onto k = +-m mod K exactly as cos(m*lon_j)
+//   does on the grid.
+//   analysis: forward FFT of f_i + i f_i', split into the two real spectra, de-twist, quadrature weights, E/O.
+// Algorithm: in-place mixed-radix (8,4,2,3,5) Cooley-Tukey in shared memory, one buffer per transform (16 B/point,
+// index skewed by i>>3 against bank conflicts): decimation in time for synthesis (spectrum written straight to its
+// digit-reversed slot, natural-order output -> coalesced row stores), decimation in frequency for analysis (natural
+// input, spectrum picked up from the digit-reversed slots).  NF consecutive fields of one latitude pair per CTA so that
+// every G access is a full 64 B segment.
+#include "internal.h"
+
+namespace shb {
+namespace fft {
+
+constexpr int NTHREADS = 512;
+constexpr int MAXRAD = 16;
+
+struct Params {
+    int K, nrad, NF, TPT, stride;
+    int rad[MAXRAD];   // DIT order (first pass has sub-transform length 1)
+    int ns[MAXRAD];    // product of the previous radices
+};
+
+__device__ __forceinline__ int padi(int i) { return i + (i >> 3); }
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
+// multiply by s*i
+__device__ __forceinline__ double2 mul_si(double2 a, double s) { return make_double2(-s * a.y, s * a.x); }
+
+// length-R DFT in registers, X[k] = sum_n v[n] exp(s*2*pi*i*n*k/R); s = -1 forward, +1 inverse
+template <int R>
+__device__ __forceinline__ void dft(double2* v, double s);
+
+template <>
+__device__ __forceinline__ void dft<2>(double2* v, double) {
+    double2 a = v[0], b = v[1];
+    v[0] = cadd(a, b); v[1] = csub(a, b);
+}
+__device__ __forceinline__ void dft4(double2& b0, double2& b1, double2& b2, double2& b3, double s) {
+    double2 p = cadd(b0, b2), q = csub(b0, b2), r = cadd(b1, b3), t = mul_si(csub(b1, b3), s);
+    b0 = cadd(p, r); b2 = csub(p, r); b1 = cadd(q, t); b3 = csub(q, t);
+}
+template <>
+__device__ __forceinline__ void dft<4>(double2* v, double s) { dft4(v[0], v[1], v[2], v[3], s); }
+template <>
+__device__ __forceinline__ void dft<8>(double2* v, double s) {
+    const double h = 0.70710678118654752440;
+    double2 a0 = cadd(v[0], v[4]), c0 = csub(v[0], v[4]);
+    double2 a1 = cadd(v[1], v[5]), c1 = csub(v[1], v[5]);
+    double2 a2 = cadd(v[2], v[6]), c2 = csub(v[2], v[6]);
+    double2 a3 = cadd(v[3], v[7]), c3 = csub(v[3], v[7]);
+    // c_n *= w8^n, w8 = exp(s*i*pi/4)
+    c1 = make_double2(h * (c1.x - s * c1.y), h * (c1.y + s * c1.x));
+    c2 = mul_si(c2, s);
+    c3 = make_double2(h * (-c3.x - s * c3.y), h * (-c3.y + s * c3.x));
+    dft4(a0, a1, a2, a3, s);
+    dft4(c0, c1, c2, c3, s);
+    v[0] = a0; v[2] = a1; v[4] = a2; v[6] = a3;
+    v[1] = c0; v[3] = c1; v[5] = c2; v[7] = c3;
+}
+template <>
+__device__ __forceinline__ void dft<3>(double2* v, double s) {
+    const double c3 = -0.5, s3 = 0.86602540378443864676;
+    double2 t1 = cadd(v[1], v[2]);
+    double2 t2 = make_double2(v[0].x + c3 * t1.x, v[0].y + c3 * t1.y);
+    double2 u = mul_si(csub(v[1], v[2]), s * s3);
+    v[0] = cadd(v[0], t1); v[1] = cadd(t2, u); v[2] = csub(t2, u);
+}
+template <>
+__device__ __forceinline__ void dft<5>(double2* v, double s) {
+    const double c1 = 0.30901699437494742410, c2 = -0.80901699437494742410;
+    const double s1 = 0.95105651629515357212, s2 = 0.58778525229247312917;
+    double2 a1 = cadd(v[1], v[4]), b1 = csub(v[1], v[4]);
+    double2 a2 = cadd(v[2], v[3]), b2 = csub(v[2], v[3]);
+    double2 m1 = make_double2(v[0].x + c1 * a1.x + c2 * a2.x, v[0].y + c1 * a1.y + c2 * a2.y);
+    double2 m2 = make_double2(v[0].x + c2 * a1.x + c1 * a2.x, v[0].y + c2 * a1.y + c1 * a2.y);
+    double2 u1 = mul_si(make_double2(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y), s);
+    double2 u2 = mul_si(make_double2(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y), s);
+    v[0] = cadd(v[0], cadd(a1, a2));
+    v[1] = cadd(m1, u1); v[4] = csub(m1, u1);
+    v[2] = cadd(m2, u2); v[3] = csub(m2, u2);
+}
+
+// powers w^1..w^(R-1) with multiplication depth <= 3
+template <int R>
+__device__ __forceinline__ void twiddle_powers(double2 w1, double2* w) {
+    w[1] = w1;
+    if (R > 2) w[2] = cmul(w1, w1);
+    if (R > 3) w[3] = cmul(w[2], w1);
+    if (R > 4) w[4] = cmul(w[2], w[2]);
+    if (R > 5) w[5] = cmul(w[4], w1);
+    if (R > 6) w[6] = cmul(w[3], w[3]);
+    if (R > 7) w[7] = cmul(w[4], w[3]);
+}
+
+// one in-place pass over one transform (buffer x, skewed indexing).  DIT: twiddle inputs; DIF: twiddle outputs.
+template <int R, bool DIT>
+__device__ __forceinline__ void pass(double2* __restrict__ x, int K, int Ns, int tpt, int lt, const double2* __restrict__ tw, double sgn) {
+    const int M = Ns * R, nb = K / R, tws = K / M;
+    for (int idx = lt; idx < nb; idx += tpt) {
+        const int g = idx / Ns, k = idx - g * Ns;
+        const int base = g * M + k;
+        double2 v[R], w[R];
+        if (k > 0) {
+            double2 w1 = tw[k * tws];
+            if (sgn > 0) w1.y = -w1.y;
+            twiddle_powers<R>(w1, w);
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) v[q] = x[padi(base + q * Ns)];
+        if (DIT && k > 0) {
+#pragma unroll
+            for (int q = 1; q < R; ++q) v[q] = cmul(v[q], w[q]);
+        }
+        dft<R>(v, sgn);
+        if (!DIT && k > 0) {
+#pragma unroll
+            for (int q = 1; q < R; ++q) v[q] = cmul(v[q], w[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) x[padi(base + q * Ns)] = v[q];
+    }
+}
+
+template <bool DIT>
+__device__ __forceinline__ void run_pass(int R, double2* x, int K, int Ns, int tpt, int lt, const double2* tw, double sgn) {
+    if (R == 8) pass<8, DIT>(x, K, Ns, tpt, lt, tw, sgn);
+    else if (R == 4) pass<4, DIT>(x, K, Ns, tpt, lt, tw, sgn);
+    else if (R == 2) pass<2, DIT>(x, K, Ns, tpt, lt, tw, sgn);
+    else if (R == 3) pass<3, DIT>(x, K, Ns, tpt, lt, tw, sgn);
+    else pass<5, DIT>(x, K, Ns, tpt, lt, tw, sgn);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 1) k_lon_syn_fft(DevTables t, Params fp, const int* __restrict__ perm, int batch, const double* __restrict__ G,
+                                                             double* __restrict__ grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon) {
+    extern __shared__ double2 smem2[];
+    const int K = fp.K, N = t.nmax, R = t.nrows, NC = t.NC, Bp = t.Bp, NF = fp.NF;
+    const int row = blockIdx.x, b0 = blockIdx.y * NF;
+    const int tid = threadIdx.x;
+    const int i1 = t.row_i1[row], i2 = t.row_i2[row];
+    const bool mirror = i2 >= 0;
+    for (int i = tid; i < NF * fp.stride; i += NTHREADS) smem2[i] = make_double2(0.0, 0.0);
+    __syncthreads();
+    // ---- spectrum assembly: thread <-> (order m, field), fields fastest
+    const bool simple = 2 * N < K;
+    const int nrounds = simple ? 1 : (N + K) / K;
+    for (int rnd = 0; rnd < nrounds; ++rnd) {
+        const int mlo = rnd * K, mhi = min(N, mlo + K - 1);
+        for (int sub = 0; sub < (simple ? 1 : 2); ++sub) {
+            for (int idx = tid; idx < (mhi - mlo + 1) * NF; idx += NTHREADS) {
+                const int mm = idx / NF, f = idx - mm * NF;
+                const int m = mlo + mm, b = b0 + f;
+                if (b >= batch) continue;
+                const double* g = G + (((int64_t)m * R + row) * 2) * NC + b;
+                const double Ec = g[0], Es = g[Bp], Oc = g[NC], Os = g[NC + Bp];
+                const double2 ph = t.phase[m];
+                const double2 Z = cmul(make_double2(Ec + Oc, -(Es + Os)), ph);                       // (A - iB) e^{i m lon0}, primary row
+                const double2 Zp = mirror ? cmul(make_double2(Ec - Oc, -(Es - Os)), ph) : make_double2(0.0, 0.0);
+                const double2 Wa = make_double2(0.5 * (Z.x - Zp.y), 0.5 * (Z.y + Zp.x));              // (Z + i Z')/2        -> k =  m mod K
+                const double2 Wb = make_double2(0.5 * (Z.x + Zp.y), 0.5 * (-Z.y + Zp.x));             // (conj Z + i conj Z')/2 -> k = -m mod K
+                double2* x = smem2 + (size_t)f * fp.stride;
+                const int k = mm, kc = (K - mm) % K;
+                if (simple) {
+                    if (k == 0) x[padi(perm[0])] = cadd(Wa, Wb);
+                    else { x[padi(perm[k])] = Wa; x[padi(perm[kc])] = Wb; }
+                } else if (sub == 0) {
+                    double2* p = &x[padi(perm[k])]; *p = cadd(*p, Wa);
+                } else {
+                    double2* p = &x[padi(perm[kc])]; *p = cadd(*p, Wb);
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // ---- inverse FFT (decimation in time)
+    const int tr = tid / fp.TPT, lt = tid - tr * fp.TPT;
+    double2* x = smem2 + (size_t)tr * fp.stride;
+    for (int s = 0; s < fp.nrad; ++s) {
+        run_pass<true>(fp.rad[s], x, K, fp.ns[s], fp.TPT, lt, t.tw, +1.0);
+        __syncthreads();
+    }
+    // ---- store: real part -> primary latitude, imaginary part -> mirror latitude
+    const int b = b0 + tr;
+    if (b < batch) {
+        double* o1 = grid + (int64_t)b * gs_b + (int64_t)i1 * gs_lat;
+        double* o2 = grid + (int64_t)b * gs_b + (int64_t)(mirror ? i2 : 0) * gs_lat;
+        for (int j = lt; j < K; j += fp.TPT) {
+            const double2 v = x[padi(j)];
+            o1[(int64_t)j * gs_lon] = v.x;
+            if (mirror) o2[(int64_t)j * gs_lon] = v.y;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) k_lon_ana_fft(DevTables t, Params fp, const int* __restrict__ perm, int batch, const double* __restrict__ grid,
+                                                             int64_t gs_b, int64_t gs_lat, int64_t gs_lon, double* __restrict__ G) {
+    extern __shared__ double2 smem2[];
+    const int K = fp.K, N = t.nmax, R = t.nrows, NC = t.NC, Bp = t.Bp, NF = fp.NF;
+    const int row = blockIdx.x, b0 = blockIdx.y * NF;
+    const int tid = threadIdx.x;
+    const int i1 = t.row_i1[row], i2 = t.row_i2[row];
+    const bool mirror = i2 >= 0;
+    const double w1 = t.w1[row], w2 = t.w2[row];
+    const int tr = tid / fp.TPT, lt = tid - tr * fp.TPT;
+    double2* x = smem2 + (size_t)tr * fp.stride;
+    {
+        const int b = b0 + tr;
+        const bool live = b < batch;
+        const double* f1 = grid + (int64_t)b * gs_b + (int64_t)i1 * gs_lat;
+        const double* f2 = grid + (int64_t)b * gs_b + (int64_t)(mirror ? i2 : 0) * gs_lat;
+        for (int j = lt; j < K; j += fp.TPT) {
+            double2 v = make_double2(0.0, 0.0);
+            if (live) { v.x = f1[(int64_t)j * gs_lon]; if (mirror) v.y = f2[(int64_t)j * gs_lon]; }
+            x[padi(j)] = v;
+        }
+    }
+    __syncthreads();
+    for (int s = fp.nrad - 1; s >= 0; --s) {
+        run_pass<false>(fp.rad[s], x, K, fp.ns[s], fp.TPT, lt, t.tw, -1.0);
+        __syncthreads();
+    }
+    for (int idx = tid; idx < (N + 1) * NF; idx += NTHREADS) {
+        const int m = idx / NF, f = idx - m * NF;
+        const int b = b0 + f;
+        if (b >= Bp) continue;
+        const double2* xx = smem2 + (size_t)f * fp.stride;
+        const int k = m % K, kc = (K - k) % K;
+        const double2 Wk = xx[padi(perm[k])], Wc = cconj(xx[padi(perm[kc])]);
+        const double2 F = make_double2(0.5 * (Wk.x + Wc.x), 0.5 * (Wk.y + Wc.y));      // spectrum of the primary row
+        const double2 D = csub(Wk, Wc);
+        const double2 Fp = make_double2(0.5 * D.y, -0.5 * D.x);                        // (Wk - conj W_{K-k}) / (2i): mirror row
+        const double2 phc = cconj(t.phase[m]);
+        const double2 Z = cmul(F, phc), Zp = cmul(Fp, phc);                            // a_m - i b_m
+        const double a = w1 * Z.x, bb = -w1 * Z.y, ap = w2 * Zp.x, bp = -w2 * Zp.y;
+        double* g = G + (((int64_t)m * R + row) * 2) * NC + b;
+        const bool live = b < batch;
+        g[0] = live ? a + ap : 0.0; g[Bp] = live ? bb + bp : 0.0;
+        g[NC] = live ? a - ap : 0.0; g[NC + Bp] = live ? bb - bp : 0.0;
+    }
+}
+
+}  // namespace fft
+
+// ---- host side ---------------------------------------------------------------------------------
+static bool fft_params(int K, int Bp, fft::Params& fp) {
+    int k = K, n = 0;
+    int rad[fft::MAXRAD];
+    while (k % 8 == 0 && n < fft::MAXRAD) { rad[n++] = 8; k /= 8; }
+    while (k % 4 == 0 && n < fft::MAXRAD) { rad[n++] = 4; k /= 4; }
+    while (k % 2 == 0 && n < fft::MAXRAD) { rad[n++] = 2; k /= 2; }
+    while (k % 3 == 0 && n < fft::MAXRAD) { rad[n++] = 3; k /= 3; }
+    while (k % 5 == 0 && n < fft::MAXRAD) { rad[n++] = 5; k /= 5; }
+    if (k != 1) return false;
+    fp.K = K; fp.nrad = n;
+    int ns = 1;
+    for (int i = 0; i < n; ++i) { fp.rad[i] = rad[i]; fp.ns[i] = ns; ns *= rad[i]; }
+    fp.stride = K + (K >> 3) + 1;
+    const size_t limit = 220 * 1024;
+    int nf = 0;
+    for (int c = 1; c <= 8 && c <= Bp; c *= 2)
+        if ((size_t)c * fp.stride * sizeof(double2) <= limit) nf = c;
+    if (nf == 0) return false;
+    fp.NF = nf; fp.TPT = fft::NTHREADS / nf;
+    return true;
+}
+
+bool lon_fft_supported(int K, int Bp) {
+    fft::Params fp;
+    return fft_params(K, Bp, fp);
+}
+
+// digit-reversal table matching the pass order of fft_params (position of spectral index k in the buffer)
+void lon_fft_perm(int K, int Bp, std::vector<int>& perm) {
+    fft::Params fp;
+    perm.assign(K, 0);
+    if (!fft_params(K, Bp, fp)) return;
+    for (int k = 0; k < K; ++k) {
+        int n = k, pos = 0;
+        for (int s = fp.nrad - 1; s >= 0; --s) { int q = n % fp.rad[s]; n /= fp.rad[s]; pos += q * fp.ns[s]; }
+        perm[k] = pos;
+    }
+}
+
+int launch_lon_syn_fft(const Plan& p, int batch, double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, cudaStream_t st) {
+    fft::Params fp;
+    fft_params(p.K, p.Bp, fp);
+    size_t smem = (size_t)fp.NF * fp.stride * sizeof(double2);
+    static bool attr = false;
+    if (!attr) { SHB_CUDA(cudaFuncSetAttribute(fft::k_lon_syn_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+    dim3 g(p.nrows, (batch + fp.NF - 1) / fp.NF);
+    fft::k_lon_syn_fft<<<g, fft::NTHREADS, smem, st>>>(p.t, fp, p.fft_perm, batch, p.G, grid, gs_b, gs_lat, gs_lon);
+    return 0;
+}
+
+int launch_lon_ana_fft(const Plan& p, int batch, const double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, cudaStream_t st) {
+    fft::Params fp;
+    fft_params(p.K, p.Bp, fp);
+    size_t smem = (size_t)fp.NF * fp.stride * sizeof(double2);
+    static bool attr = false;
+    if (!attr) { SHB_CUDA(cudaFuncSetAttribute(fft::k_lon_ana_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+    dim3 g(p.nrows, (p.Bp + fp.NF - 1) / fp.NF);
+    fft::k_lon_ana_fft<<<g, fft::NTHREADS, smem, st>>>(p.t, fp, p.fft_perm, batch, grid, gs_b, gs_lat, gs_lon, p.G);
+    return 0;
+}
+
+}  // namespace shb

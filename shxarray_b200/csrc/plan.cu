@@ -49,16 +49,6 @@ static int dev_alloc(Plan& p, size_t bytes, void** out) {
 
 void launch_ptab_gen(const Plan& p, cudaStream_t st);
 
-static bool factor235(int K, std::vector<int>& radices) {
-    radices.clear();
-    int k = K;
-    while (k % 4 == 0) { radices.push_back(4); k /= 4; }
-    while (k % 2 == 0) { radices.push_back(2); k /= 2; }
-    while (k % 3 == 0) { radices.push_back(3); k /= 3; }
-    while (k % 5 == 0) { radices.push_back(5); k /= 5; }
-    return k == 1;
-}
-
 static double ulp_scale(double x) { return std::ldexp(1.0, -52) * std::fmax(std::fabs(x), 1.0); }
 
 static int build_plan(const shb200_plan_desc& d, Plan& p) {
@@ -192,17 +182,14 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
     p.K = d.nlon;
     p.lon_fft = false;
     double lon0 = d.lon_deg[0];
-    if (d.mode == SHB200_MODE_GRID && !(d.flags & SHB200_FLAG_DENSE_LON) && d.nlon >= 2 && factor235(d.nlon, p.radices)) {
+    if (d.mode == SHB200_MODE_GRID && !(d.flags & SHB200_FLAG_DENSE_LON) && d.nlon >= 2 && lon_fft_supported(d.nlon, p.Bp)) {
         bool uniform = true;
         long double step = 360.0L / d.nlon;
         for (int j = 0; j < d.nlon && uniform; ++j) {
             long double ideal = (long double)lon0 + j * step;
             if (fabsl((long double)d.lon_deg[j] - ideal) > 8.0L * ulp_scale(d.lon_deg[j])) uniform = false;
         }
-        if (uniform) {
-            p.fft_ntrans = lon_fft_pick_ntrans(p.K, p.Bp);
-            if (p.fft_ntrans >= 1) p.lon_fft = true;
-        }
+        if (uniform) p.lon_fft = true;
     }
     std::vector<double2> tw, phase;
     std::vector<double> lonr(d.nlon);
@@ -243,6 +230,11 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
     if ((rc = upload(p, tw, &t.tw))) return rc;
     if ((rc = upload(p, phase, &t.phase))) return rc;
     if ((rc = upload(p, lonr, &t.lonr))) return rc;
+    if (p.lon_fft) {
+        std::vector<int> perm;
+        lon_fft_perm(p.K, p.Bp, perm);
+        if ((rc = upload(p, perm, &p.fft_perm))) return rc;
+    }
     if ((rc = upload(p, slot_src, &t.slot_src))) return rc;
     p.ndup = (int64_t)dup_slot.size();
     if ((rc = upload(p, dup_slot, &p.dup_slot))) return rc;
