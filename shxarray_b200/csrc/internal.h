@@ -82,6 +82,7 @@ struct Plan {
     int64_t ndup = 0;
     const int64_t* dup_slot = nullptr;  // device [ndup] slot*2+cs
     const int64_t* dup_src = nullptr;   // device [ndup]
+    const int64_t* fwd_slot = nullptr;  // device [nsh] list index -> slot*2+cs (-1 for repeated entries)
     // staging for the *_host entry points
     double* stage_coef = nullptr; int64_t stage_coef_elems = 0;
     double* stage_grid = nullptr; int64_t stage_grid_elems = 0;

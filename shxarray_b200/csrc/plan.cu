@@ -86,8 +86,9 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
 
     // ---- nm list -> slot map -----------------------------------------------------------------
     std::vector<int64_t> slot_src((size_t)T * 2, -1);
-    std::vector<int64_t> dup_slot, dup_src;
+    std::vector<int64_t> dup_slot, dup_src, fwd;
     if (d.nsh > 0) {
+        fwd.assign((size_t)d.nsh, -1);
         if (!d.n || !d.m) { set_error("plan_create: nsh > 0 but n/m arrays are null"); return SHB200_EINVAL; }
         p.nsh = d.nsh;
         p.full_triangle = (d.nsh == (int64_t)(N + 1) * (N + 1));
@@ -95,17 +96,19 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
             int n = d.n[k], m = d.m[k], am = m < 0 ? -m : m;
             if (n < 0 || n > N || am > n) { set_error("plan_create: (n,m) entry out of range"); return SHB200_EINVAL; }
             int64_t s = tri(n, am, N) * 2 + (m < 0 ? 1 : 0);
-            if (slot_src[s] < 0) slot_src[s] = k;
+            if (slot_src[s] < 0) { slot_src[s] = k; fwd[k] = s; }
             else { dup_slot.push_back(s); dup_src.push_back(k); }
             if (p.full_triangle && k != (int64_t)n * n + n + m) p.full_triangle = false;
         }
     } else {
         p.nsh = (int64_t)(N + 1) * (N + 1);
         p.full_triangle = true;
+        fwd.assign((size_t)p.nsh, -1);
         for (int n = 0; n <= N; ++n)
             for (int m = -n; m <= n; ++m) {
                 int am = m < 0 ? -m : m;
                 slot_src[tri(n, am, N) * 2 + (m < 0 ? 1 : 0)] = (int64_t)n * n + n + m;
+                fwd[(int64_t)n * n + n + m] = tri(n, am, N) * 2 + (m < 0 ? 1 : 0);
             }
     }
 
@@ -239,6 +242,7 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
     p.ndup = (int64_t)dup_slot.size();
     if ((rc = upload(p, dup_slot, &p.dup_slot))) return rc;
     if ((rc = upload(p, dup_src, &p.dup_src))) return rc;
+    if ((rc = upload(p, fwd, &p.fwd_slot))) return rc;
     t.nmax = N; t.nrows = R; t.nlat = d.nlat; t.nlon = d.nlon; t.Bp = p.Bp; t.NC = p.NC;
 
     void* ptr;
