@@ -1,0 +1,165 @@
+"""xarray-facing plugin: ``engine='b200'`` for shxarray's ``.sh`` accessor.
+
+Registers through the reference's own engine plugin interface (entry-point group
+``shxarray.computebackends``, pyproject.toml:41-43 of the reference; base class
+core/shcomputebase.py:1-20; loader core/shxarbase.py:240-259) as a sibling of ``engine='shlib'``
+(src/builtin_backend/shlib.pyx:24-159) and ``engine='shtns'`` (src/shtns_backend/shtns.py:287-420).
+Same method names, argument meaning and error behaviour; the accessor calls
+``da.sh.synthesis(engine='b200')``, ``da.sh.analysis(nmax, engine='b200')``,
+``da.sh.multiply(other, engine='b200')`` and everything layered on them work unchanged.
+
+This module needs xarray + shxarray at import time (it is only imported through the entry point or
+explicitly); everything below it (``engine.SHEngine``, ``capi``) works with numpy/torch alone.
+"""
+import numpy as np
+import xarray as xr
+
+from shxarray.core.cf import find_lat, find_lon, get_cfatts, get_cfglobal
+from shxarray.core.sh_indexing import SHindexBase
+from shxarray.core.shcomputebase import SHComputeBackendBase
+
+from . import capi
+from .engine import SHEngine, lonlat_grid as _lonlat_grid
+
+
+def _stack_aux(dain, keep):
+    """Stack every dimension not in ``keep`` into one leading batch axis (shtns.py:220-236 does the same, then loops
+    over fields in Python -- here the whole batch goes to the device in one call).  Returns (2-D/3-D view helper)."""
+    auxdims = [d for d in dain.dims if d not in keep]
+    if len(auxdims) > 1:
+        dain = dain.stack(auxdim=auxdims)
+        auxdim = "auxdim"
+    elif len(auxdims) == 0:
+        auxdim = "auxsingle"
+        dain = dain.expand_dims(auxdim)
+    else:
+        auxdim = auxdims[0]
+    return dain, auxdim
+
+
+def _unstack_aux(daout, auxdim):
+    if auxdim == "auxdim":
+        daout = daout.unstack(auxdim)
+    elif auxdim == "auxsingle":
+        daout = daout.squeeze(auxdim, drop=True)
+    return daout
+
+
+class B200Backend(SHComputeBackendBase):
+    _credits = "Used backend: shxarray_b200, hand-written sm_100a CUDA spherical-harmonic transform engine (libshb200)"
+
+    def __init__(self, device=0):
+        super().__init__()
+        capi.lib()   # fail loudly if the CUDA library is missing: there is no CPU fallback
+        self._engine = SHEngine(device=device)
+
+    # ------------------------------------------------------------------------------------------
+    def lonlat_grid(self, nmax=None, lon=None, lat=None, gtype=None):
+        """Create a lon/lat grid for this backend.  gtype: 'gauss' (default), 'regular', 'regular_lon0' (identical to
+        shlib.pyx:87-96) or 'point'.  Sets ``shxarray_gtype`` on both coordinates (shlib.pyx:115-116)."""
+        if gtype is None:
+            gtype = "gauss"
+        if lon is not None and hasattr(lon, "data"):
+            lon = lon.data
+        if lat is not None and hasattr(lat, "data"):
+            lat = lat.data
+        g = _lonlat_grid(nmax=nmax, lon=lon, lat=lat, gtype=gtype)
+        if gtype == "point":
+            dslonlat = xr.Dataset(coords=dict(lon=("nlonlat", g["lon"]), lat=("nlonlat", g["lat"])))
+        else:
+            dslonlat = xr.Dataset(coords=dict(lon=g["lon"], lat=g["lat"]))
+        dslonlat.lon.attrs.update(get_cfatts("longitude"))
+        dslonlat.lat.attrs.update(get_cfatts("latitude"))
+        dslonlat.lon.attrs["shxarray_gtype"] = gtype
+        dslonlat.lat.attrs["shxarray_gtype"] = gtype
+        return dslonlat
+
+    # ------------------------------------------------------------------------------------------
+    def synthesis(self, dain, dslonlat, **kwargs):
+        if type(dain) != xr.DataArray:
+            raise RuntimeError("input type should be a xarray.DataArray")
+        if "nm" not in dain.indexes:
+            raise RuntimeError("Spherical harmonic index not found in input, cannot apply synthesis operator to object")
+        loninfo = find_lon(dslonlat.coords)
+        latinfo = find_lat(dslonlat.coords)
+        lon = np.asarray(loninfo.var.data, dtype=np.float64)
+        lat = np.asarray(latinfo.var.data, dtype=np.float64)
+        points = latinfo.var.dims[0] == loninfo.var.dims[0]      # synthesis.pyx:92-98
+        n = dain.nm.n.data.astype(np.int32)
+        m = dain.nm.m.data.astype(np.int32)
+        name = dain.name
+        dast, auxdim = _stack_aux(dain, ["nm"])
+        dast = dast.transpose(auxdim, "nm")
+        coef = np.asarray(dast.data, dtype=np.float64)           # [B, nsh], any strides
+        out = self._engine.synthesis(coef, n, m, lon, lat, points=points)
+        if points:
+            pdim = latinfo.var.dims[0]
+            coords = {auxdim: dast.coords[auxdim], "lat": (pdim, lat), "lon": (pdim, lon)}
+            daout = xr.DataArray(out, coords=coords, dims=[auxdim, pdim])
+        else:
+            coords = {auxdim: dast.coords[auxdim], "lat": lat, "lon": lon}
+            daout = xr.DataArray(out, coords=coords, dims=[auxdim, "lat", "lon"])
+        daout = _unstack_aux(daout, auxdim)
+        daout.name = name
+        daout.lon.attrs = dict(get_cfatts("longitude"))
+        daout.lat.attrs = dict(get_cfatts("latitude"))
+        for c in ("lon", "lat"):
+            if "shxarray_gtype" in dslonlat[c].attrs:
+                daout[c].attrs["shxarray_gtype"] = dslonlat[c].attrs["shxarray_gtype"]
+        daout.attrs.update(get_cfglobal())
+        daout.attrs["history"] = "Synthesis performed using b200 backend"
+        daout.attrs["comments"] = self._credits
+        return daout
+
+    # ------------------------------------------------------------------------------------------
+    def analysis(self, dain, nmax, quadrature=None, **kwargs):
+        """quadrature: None -> 'gauss' if the grid carries shxarray_gtype='gauss', else 'shlib' (midpoint weights, the
+        values shlib itself produces: analysis.pyx:57-60,129)."""
+        if type(dain) != xr.DataArray:
+            raise RuntimeError("input type should be a xarray.DataArray")
+        loninfo = find_lon(dain.coords)
+        latinfo = find_lat(dain.coords)
+        gtype = loninfo.var.attrs.get("shxarray_gtype", None)
+        if quadrature is None:
+            quadrature = "gauss" if gtype == "gauss" else "shlib"
+        if quadrature == "shlib" and (loninfo.step is None or latinfo.step is None):
+            raise RuntimeError("grid is not equidistant in lon and lat directions")
+        if latinfo.var.dims[0] == loninfo.var.dims[0]:
+            raise RuntimeError("Analysis is not supported for point grids")
+        lonname, latname = loninfo.var.dims[0], latinfo.var.dims[0]
+        name = dain.name
+        dast, auxdim = _stack_aux(dain, [lonname, latname])
+        dast = dast.transpose(auxdim, latname, lonname)          # a view: strides go straight to the C ABI
+        grid = np.asarray(dast.data, dtype=np.float64)
+        lon = np.asarray(loninfo.var.data, dtype=np.float64)
+        lat = np.asarray(latinfo.var.data, dtype=np.float64)
+        out = self._engine.analysis(grid, int(nmax), lon, lat, quadrature=quadrature)
+        coords = {auxdim: dast.coords[auxdim], SHindexBase.name: SHindexBase.nm_mi(int(nmax), 0)}
+        daout = xr.DataArray(out, coords=coords, dims=[auxdim, SHindexBase.name])
+        daout = _unstack_aux(daout, auxdim)
+        daout.name = name
+        daout.attrs.update(get_cfglobal())
+        daout.attrs["history"] = "Analysis performed using b200 backend"
+        daout.attrs["comments"] = self._credits
+        return daout
+
+    # ------------------------------------------------------------------------------------------
+    def multiply(self, dash1, dash2, **kwargs):
+        """Product of two SH fields through the spatial domain (shtns.py:394-420): Gauss grid of nmax1+nmax2,
+        two syntheses, pointwise product, Gauss-quadrature analysis."""
+        nmax = dash1.sh.nmax + dash2.sh.nmax
+        dslonlat = self.lonlat_grid(nmax=nmax, gtype="gauss")
+        dagrd1 = self.synthesis(dash1, dslonlat)
+        dagrd2 = self.synthesis(dash2, dslonlat)
+        dagrd = dagrd1 * dagrd2
+        dagrd.lon.attrs["shxarray_gtype"] = "gauss"
+        dagrd.lat.attrs["shxarray_gtype"] = "gauss"
+        return self.analysis(dagrd, nmax=nmax, quadrature="gauss")
+
+
+def register(name="b200", device=0):
+    """Make the engine available as ``engine=name`` without installing entry-point metadata (tests, notebooks):
+    inserts an instance into shxarray's engine cache (core/shxarbase.py:14,255)."""
+    from shxarray.core import shxarbase
+    shxarbase.loaded_engines[name] = B200Backend(device=device)
+    return shxarbase.loaded_engines[name]
