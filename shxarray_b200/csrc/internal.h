@@ -43,7 +43,12 @@ struct DevTables {
     // nm packing
     const int64_t* slot_src;  // [tri_size*2] index into the user nm list for (slot, cos/sin) or -1
     int nmax, nrows, nlat, nlon, Bp, NC;
+    int GS;               // field-group size of the column order (8, or 4 for tiny batches)
 };
+
+// Column of (cos/sin cs, field b) inside a Cm / G row: fields come in groups of GS with the cosine and sine part of a
+// group adjacent, [b/GS][cs][b%GS], so that the longitude stage (GS fields per CTA) touches full 128-byte lines.
+__host__ __device__ inline int colidx(int cs, int b, int GS) { return (b / GS) * (2 * GS) + cs * GS + (b % GS); }
 
 struct Plan;
 

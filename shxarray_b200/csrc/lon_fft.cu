@@ -157,26 +157,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lon_syn_fft(DevTables t, Params
     for (int rnd = 0; rnd < nrounds; ++rnd) {
         const int mlo = rnd * K, mhi = min(N, mlo + K - 1);
         for (int sub = 0; sub < (simple ? 1 : 2); ++sub) {
-            for (int idx = tid; idx < (mhi - mlo + 1) * NF; idx += NTHREADS) {
-                const int mm = idx / NF, f = idx - mm * NF;
-                const int m = mlo + mm, b = b0 + f;
-                if (b >= batch) continue;
-                const double* g = G + (((int64_t)m * R + row) * 2) * NC + b;
-                const double Ec = g[0], Es = g[Bp], Oc = g[NC], Os = g[NC + Bp];
-                const double2 ph = t.phase[m];
-                const double2 Z = cmul(make_double2(Ec + Oc, -(Es + Os)), ph);                       // (A - iB) e^{i m lon0}, primary row
-                const double2 Zp = mirror ? cmul(make_double2(Ec - Oc, -(Es - Os)), ph) : make_double2(0.0, 0.0);
-                const double2 Wa = make_double2(0.5 * (Z.x - Zp.y), 0.5 * (Z.y + Zp.x));              // (Z + i Z')/2        -> k =  m mod K
-                const double2 Wb = make_double2(0.5 * (Z.x + Zp.y), 0.5 * (-Z.y + Zp.x));             // (conj Z + i conj Z')/2 -> k = -m mod K
-                double2* x = smem2 + (size_t)f * fp.stride;
-                const int k = mm, kc = (K - mm) % K;
-                if (simple) {
-                    if (k == 0) x[padi(perm[0])] = cadd(Wa, Wb);
-                    else { x[padi(perm[k])] = Wa; x[padi(perm[kc])] = Wb; }
-                } else if (sub == 0) {
-                    double2* p = &x[padi(perm[k])]; *p = cadd(*p, Wa);
-                } else {
-                    double2* p = &x[padi(perm[kc])]; *p = cadd(*p, Wb);
+            const int nitems = (mhi - mlo + 1) * NF;
+            constexpr int UN = 4;                       // independent (order, field) items in flight per thread
+            for (int base = tid; base < nitems; base += NTHREADS * UN) {
+                double Ec[UN], Es[UN], Oc[UN], Os[UN];
+                double2 ph[UN];
+                bool ok[UN];
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    const int idx = base + u * NTHREADS;
+                    const int mm = idx / NF, f = idx - mm * NF;
+                    ok[u] = idx < nitems && b0 + f < batch;
+                    if (ok[u]) {
+                        const double* g = G + (((int64_t)(mlo + mm) * R + row) * 2) * NC + colidx(0, b0 + f, t.GS);
+                        Ec[u] = g[0]; Es[u] = g[t.GS]; Oc[u] = g[NC]; Os[u] = g[NC + t.GS];
+                        ph[u] = t.phase[mlo + mm];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    if (!ok[u]) continue;
+                    const int idx = base + u * NTHREADS;
+                    const int mm = idx / NF, f = idx - mm * NF;
+                    const double2 Z = cmul(make_double2(Ec[u] + Oc[u], -(Es[u] + Os[u])), ph[u]);          // (A - iB) e^{i m lon0}, primary row
+                    const double2 Zp = mirror ? cmul(make_double2(Ec[u] - Oc[u], -(Es[u] - Os[u])), ph[u]) : make_double2(0.0, 0.0);
+                    const double2 Wa = make_double2(0.5 * (Z.x - Zp.y), 0.5 * (Z.y + Zp.x));              // (Z + i Z')/2        -> k =  m mod K
+                    const double2 Wb = make_double2(0.5 * (Z.x + Zp.y), 0.5 * (-Z.y + Zp.x));             // (conj Z + i conj Z')/2 -> k = -m mod K
+                    double2* x = smem2 + (size_t)f * fp.stride;
+                    const int k = mm, kc = (K - mm) % K;
+                    if (simple) {
+                        if (k == 0) x[padi(perm[0])] = cadd(Wa, Wb);
+                        else { x[padi(perm[k])] = Wa; x[padi(perm[kc])] = Wb; }
+                    } else if (sub == 0) {
+                        double2* p = &x[padi(perm[k])]; *p = cadd(*p, Wa);
+                    } else {
+                        double2* p = &x[padi(perm[kc])]; *p = cadd(*p, Wb);
+                    }
                 }
             }
             __syncthreads();
@@ -242,10 +258,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lon_ana_fft(DevTables t, Params
         const double2 phc = cconj(t.phase[m]);
         const double2 Z = cmul(F, phc), Zp = cmul(Fp, phc);                            // a_m - i b_m
         const double a = w1 * Z.x, bb = -w1 * Z.y, ap = w2 * Zp.x, bp = -w2 * Zp.y;
-        double* g = G + (((int64_t)m * R + row) * 2) * NC + b;
+        double* g = G + (((int64_t)m * R + row) * 2) * NC + colidx(0, b, t.GS);
         const bool live = b < batch;
-        g[0] = live ? a + ap : 0.0; g[Bp] = live ? bb + bp : 0.0;
-        g[NC] = live ? a - ap : 0.0; g[NC + Bp] = live ? bb - bp : 0.0;
+        g[0] = live ? a + ap : 0.0; g[t.GS] = live ? bb + bp : 0.0;
+        g[NC] = live ? a - ap : 0.0; g[NC + t.GS] = live ? bb - bp : 0.0;
     }
 }
 

@@ -78,7 +78,7 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
     SHB_CUDA(cudaSetDevice(d.device));
 
     p.device = d.device; p.nmax = d.nmax; p.maxB = d.max_batch;
-    p.Bp = (d.max_batch + 3) / 4 * 4;           // columns come in blocks of 8 = (cos,sin) x 4 fields
+    p.Bp = d.max_batch <= 4 ? 4 : (d.max_batch + 7) / 8 * 8;   // columns come in blocks of 2*GS = (cos,sin) x GS fields
     p.NC = 2 * p.Bp;
     p.mode = d.mode; p.nlat = d.nlat; p.nlon = d.nlon; p.quadrature = d.quadrature; p.flags = d.flags;
     const int N = d.nmax;
@@ -243,7 +243,7 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
     if ((rc = upload(p, dup_slot, &p.dup_slot))) return rc;
     if ((rc = upload(p, dup_src, &p.dup_src))) return rc;
     if ((rc = upload(p, fwd, &p.fwd_slot))) return rc;
-    t.nmax = N; t.nrows = R; t.nlat = d.nlat; t.nlon = d.nlon; t.Bp = p.Bp; t.NC = p.NC;
+    t.nmax = N; t.nrows = R; t.nlat = d.nlat; t.nlon = d.nlon; t.Bp = p.Bp; t.NC = p.NC; t.GS = p.Bp >= 8 ? 8 : 4;
 
     void* ptr;
     if ((rc = dev_alloc(p, sizeof(double) * (size_t)T * p.NC, &ptr))) return rc;
