@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(ts::NTHREADS, 1) k_leg_syn_tab(DevTables t, co
     const int nchunks = (N - m + CH) / CH;
     const int64_t tmm = tri(m, m, N);
 
-    for (int i = tid; i < (int)(sizeof(Stage) * STAGES / 8); i += NTHREADS) reinterpret_cast<double*>(smraw)[i] = 0.0;
+    // no zero fill of the ring: fragments of degrees beyond nmax are masked in the consumers (0 x stale NaN would poison)
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCONS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(ts::NTHREADS, 1) k_leg_syn_tab(DevTables t, co
 #pragma unroll
                     for (int g = 0; g < 4; ++g) A[g] = j < valid ? S.P[j][32 * wr + 8 * g + lr] : 0.0;   // rows beyond nmax hold stale data
 #pragma unroll
-                    for (int cb = 0; cb < 4; ++cb) B[cb] = S.C[j][32 * wc + 8 * cb + lr];
+                    for (int cb = 0; cb < 4; ++cb) B[cb] = j < valid ? S.C[j][32 * wc + 8 * cb + lr] : 0.0;
 #pragma unroll
                     for (int g = 0; g < 4; ++g)
 #pragma unroll
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(ta::NTHREADS, 1) k_leg_ana_tab(DevTables t, co
     const int nrt = (R + RT - 1) / RT;
     const int64_t tmm = tri(m, m, N);
 
-    for (int i = tid; i < (int)((sizeof(GTile) * 2 + sizeof(PTile) * PSTAGES) / 8); i += NTHREADS) reinterpret_cast<double*>(smraw)[i] = 0.0;
+    // no zero fill: rows beyond the last latitude row and degrees beyond nmax are masked in the consumers
     if (tid == 0) {
         for (int s = 0; s < PSTAGES; ++s) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], NCONS / 32); }
         for (int g = 0; g < 2; ++g) { mbar_init(&gfull[g], 1); mbar_init(&gempty[g], NCONS / 32); }
@@ -185,7 +185,9 @@ __global__ void __launch_bounds__(ta::NTHREADS, 1) k_leg_ana_tab(DevTables t, co
 
     if (warp == NCONS / 32) {
         // ------------------------------------------------------------------ TMA warp
+        int sidx = 0;
         for (int sb = 0; sb < nsb; ++sb) {
+            const int ninner = min(SB / NS, (N - m - sb * SB + NS) / NS);     // stages of this super-block that hold degrees <= nmax
             for (int rt = 0; rt < nrt; ++rt) {
                 const int it = sb * nrt + rt;
                 const int gb = it & 1;
@@ -198,12 +200,11 @@ __global__ void __launch_bounds__(ta::NTHREADS, 1) k_leg_ana_tab(DevTables t, co
                     bulk_g2s(&gt[gb].g[lane][0][0], src, (uint32_t)(ncols * 8), &gfull[gb]);
                     bulk_g2s(&gt[gb].g[lane][1][0], src + NC, (uint32_t)(ncols * 8), &gfull[gb]);
                 }
-                for (int inner = 0; inner < SB / NS; ++inner) {
-                    const int sidx = it * (SB / NS) + inner;
+                for (int inner = 0; inner < ninner; ++inner, ++sidx) {
                     const int s = sidx % PSTAGES;
                     mbar_wait(&pempty[s], ((sidx / PSTAGES) & 1) ^ 1);
                     const int k0 = sb * SB + inner * NS;
-                    const int valid = max(0, min(NS, N - m - k0 + 1));
+                    const int valid = min(NS, N - m - k0 + 1);
                     if (lane == 0) mbar_arrive_expect_tx(&pfull[s], (uint32_t)(valid * RT * 8));
                     __syncwarp();
                     if (lane < valid) bulk_g2s(&ptile[s].p[lane][0], Ptab + (tmm + k0 + lane) * Rpad + rt * RT, (uint32_t)(RT * 8), &pfull[s]);
@@ -215,7 +216,9 @@ __global__ void __launch_bounds__(ta::NTHREADS, 1) k_leg_ana_tab(DevTables t, co
         const int e = warp & 1, cq = warp >> 1;
         const int lr = lane >> 2, lk = lane & 3;
         double acc[8][4][2];
+        int sidx = 0;
         for (int sb = 0; sb < nsb; ++sb) {
+            const int ninner = min(SB / NS, (N - m - sb * SB + NS) / NS);
 #pragma unroll
             for (int nb = 0; nb < 8; ++nb)
 #pragma unroll
@@ -223,13 +226,15 @@ __global__ void __launch_bounds__(ta::NTHREADS, 1) k_leg_ana_tab(DevTables t, co
             for (int rt = 0; rt < nrt; ++rt) {
                 const int it = sb * nrt + rt;
                 const int gb = it & 1;
+                const int nr = min(RT, R - rt * RT);
                 mbar_wait(&gfull[gb], (it >> 1) & 1);
                 const GTile& GT = gt[gb];
 #pragma unroll
                 for (int inner = 0; inner < SB / NS; ++inner) {
-                    const int sidx = it * (SB / NS) + inner;
+                    if (inner >= ninner) break;
                     const int s = sidx % PSTAGES;
                     mbar_wait(&pfull[s], (sidx / PSTAGES) & 1);
+                    ++sidx;
                     const PTile& PT = ptile[s];
                     const int valid = N - m - (sb * SB + inner * NS) + 1;     // degrees of this stage that exist
 #pragma unroll
@@ -240,8 +245,9 @@ __global__ void __launch_bounds__(ta::NTHREADS, 1) k_leg_ana_tab(DevTables t, co
                             const int j = 16 * q + 2 * lr + e;
                             A[q] = j < valid ? PT.p[j][4 * ks + lk] : 0.0;
                         }
+                        const bool rowok = 4 * ks + lk < nr;
 #pragma unroll
-                        for (int cb = 0; cb < 4; ++cb) B[cb] = GT.g[4 * ks + lk][e][32 * cq + 8 * cb + lr];
+                        for (int cb = 0; cb < 4; ++cb) B[cb] = rowok ? GT.g[4 * ks + lk][e][32 * cq + 8 * cb + lr] : 0.0;
 #pragma unroll
                         for (int q = 0; q < 2; ++q)
 #pragma unroll

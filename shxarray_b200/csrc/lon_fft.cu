@@ -19,11 +19,11 @@
 namespace shb {
 namespace fft {
 
-constexpr int NTHREADS = 512;
+constexpr int MAXTHREADS = 512;
 constexpr int MAXRAD = 16;
 
 struct Params {
-    int K, nrad, NF, TPT, stride;
+    int K, nrad, NF, TPT, stride, nthreads;
     int rad[MAXRAD];   // DIT order (first pass has sub-transform length 1)
     int ns[MAXRAD];    // product of the previous radices
 };
@@ -103,31 +103,46 @@ __device__ __forceinline__ void twiddle_powers(double2 w1, double2* w) {
 }
 
 // one in-place pass over one transform (buffer x, skewed indexing).  DIT: twiddle inputs; DIF: twiddle outputs.
+// Butterflies are processed in chunks of UB with their twiddle loads (global, L2 latency) issued together up front.
 template <int R, bool DIT>
 __device__ __forceinline__ void pass(double2* __restrict__ x, int K, int Ns, int tpt, int lt, const double2* __restrict__ tw, double sgn) {
+    constexpr int UB = R >= 8 ? 3 : 4;
     const int M = Ns * R, nb = K / R, tws = K / M;
-    for (int idx = lt; idx < nb; idx += tpt) {
-        const int g = idx / Ns, k = idx - g * Ns;
-        const int base = g * M + k;
-        double2 v[R], w[R];
-        if (k > 0) {
-            double2 w1 = tw[k * tws];
-            if (sgn > 0) w1.y = -w1.y;
-            twiddle_powers<R>(w1, w);
+    for (int i0 = lt; i0 < nb; i0 += tpt * UB) {
+        double2 w1[UB];
+        int base[UB], kk[UB];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            const int idx = i0 + u * tpt;
+            const int g = idx / Ns, k = idx - g * Ns;
+            base[u] = idx < nb ? g * M + k : -1;
+            kk[u] = k;
+            w1[u] = (idx < nb && k > 0) ? tw[k * tws] : make_double2(1.0, 0.0);
         }
 #pragma unroll
-        for (int q = 0; q < R; ++q) v[q] = x[padi(base + q * Ns)];
-        if (DIT && k > 0) {
+        for (int u = 0; u < UB; ++u) {
+            if (base[u] < 0) continue;
+            double2 v[R], w[R];
+            const bool tw_on = kk[u] > 0;
+            if (tw_on) {
+                double2 ww = w1[u];
+                if (sgn > 0) ww.y = -ww.y;
+                twiddle_powers<R>(ww, w);
+            }
 #pragma unroll
-            for (int q = 1; q < R; ++q) v[q] = cmul(v[q], w[q]);
+            for (int q = 0; q < R; ++q) v[q] = x[padi(base[u] + q * Ns)];
+            if (DIT && tw_on) {
+#pragma unroll
+                for (int q = 1; q < R; ++q) v[q] = cmul(v[q], w[q]);
+            }
+            dft<R>(v, sgn);
+            if (!DIT && tw_on) {
+#pragma unroll
+                for (int q = 1; q < R; ++q) v[q] = cmul(v[q], w[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < R; ++q) x[padi(base[u] + q * Ns)] = v[q];
         }
-        dft<R>(v, sgn);
-        if (!DIT && k > 0) {
-#pragma unroll
-            for (int q = 1; q < R; ++q) v[q] = cmul(v[q], w[q]);
-        }
-#pragma unroll
-        for (int q = 0; q < R; ++q) x[padi(base + q * Ns)] = v[q];
     }
 }
 
@@ -141,12 +156,12 @@ __device__ __forceinline__ void run_pass(int R, double2* x, int K, int Ns, int t
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHREADS, 1) k_lon_syn_fft(DevTables t, Params fp, const int* __restrict__ perm, int batch, const double* __restrict__ G,
+__global__ void __launch_bounds__(MAXTHREADS) k_lon_syn_fft(DevTables t, Params fp, const int* __restrict__ perm, int batch, const double* __restrict__ G,
                                                              double* __restrict__ grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon) {
     extern __shared__ double2 smem2[];
     const int K = fp.K, N = t.nmax, R = t.nrows, NC = t.NC, Bp = t.Bp, NF = fp.NF;
     const int row = blockIdx.x, b0 = blockIdx.y * NF;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, NTHREADS = blockDim.x;
     const int i1 = t.row_i1[row], i2 = t.row_i2[row];
     const bool mirror = i2 >= 0;
     for (int i = tid; i < NF * fp.stride; i += NTHREADS) smem2[i] = make_double2(0.0, 0.0);
@@ -218,12 +233,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lon_syn_fft(DevTables t, Params
     }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) k_lon_ana_fft(DevTables t, Params fp, const int* __restrict__ perm, int batch, const double* __restrict__ grid,
+__global__ void __launch_bounds__(MAXTHREADS) k_lon_ana_fft(DevTables t, Params fp, const int* __restrict__ perm, int batch, const double* __restrict__ grid,
                                                              int64_t gs_b, int64_t gs_lat, int64_t gs_lon, double* __restrict__ G) {
     extern __shared__ double2 smem2[];
     const int K = fp.K, N = t.nmax, R = t.nrows, NC = t.NC, Bp = t.Bp, NF = fp.NF;
     const int row = blockIdx.x, b0 = blockIdx.y * NF;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, NTHREADS = blockDim.x;
     const int i1 = t.row_i1[row], i2 = t.row_i2[row];
     const bool mirror = i2 >= 0;
     const double w1 = t.w1[row], w2 = t.w2[row];
@@ -281,12 +296,16 @@ static bool fft_params(int K, int Bp, fft::Params& fp) {
     int ns = 1;
     for (int i = 0; i < n; ++i) { fp.rad[i] = rad[i]; fp.ns[i] = ns; ns *= rad[i]; }
     fp.stride = K + (K >> 3) + 1;
-    const size_t limit = 220 * 1024;
+    // fields per CTA: as many as fit (8 = one full 128-byte line of G per order and parity); two CTAs of 4 fields per SM
+    // measured no faster (r01: 0.61 vs 0.57 ms synthesis at cfg3)
+    const size_t per = (size_t)fp.stride * sizeof(double2);
     int nf = 0;
     for (int c = 1; c <= 8 && c <= Bp; c *= 2)
-        if ((size_t)c * fp.stride * sizeof(double2) <= limit) nf = c;
+        if (c * per <= 220 * 1024) nf = c;
     if (nf == 0) return false;
-    fp.NF = nf; fp.TPT = fft::NTHREADS / nf;
+    fp.NF = nf;
+    fp.TPT = nf >= 4 ? 64 : (nf == 2 ? 128 : 256);
+    fp.nthreads = fp.NF * fp.TPT;
     return true;
 }
 
@@ -314,7 +333,7 @@ int launch_lon_syn_fft(const Plan& p, int batch, double* grid, int64_t gs_b, int
     static bool attr = false;
     if (!attr) { SHB_CUDA(cudaFuncSetAttribute(fft::k_lon_syn_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
     dim3 g(p.nrows, (batch + fp.NF - 1) / fp.NF);
-    fft::k_lon_syn_fft<<<g, fft::NTHREADS, smem, st>>>(p.t, fp, p.fft_perm, batch, p.G, grid, gs_b, gs_lat, gs_lon);
+    fft::k_lon_syn_fft<<<g, fp.nthreads, smem, st>>>(p.t, fp, p.fft_perm, batch, p.G, grid, gs_b, gs_lat, gs_lon);
     return 0;
 }
 
@@ -325,7 +344,7 @@ int launch_lon_ana_fft(const Plan& p, int batch, const double* grid, int64_t gs_
     static bool attr = false;
     if (!attr) { SHB_CUDA(cudaFuncSetAttribute(fft::k_lon_ana_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
     dim3 g(p.nrows, (p.Bp + fp.NF - 1) / fp.NF);
-    fft::k_lon_ana_fft<<<g, fft::NTHREADS, smem, st>>>(p.t, fp, p.fft_perm, batch, grid, gs_b, gs_lat, gs_lon, p.G);
+    fft::k_lon_ana_fft<<<g, fp.nthreads, smem, st>>>(p.t, fp, p.fft_perm, batch, grid, gs_b, gs_lat, gs_lon, p.G);
     return 0;
 }
 
