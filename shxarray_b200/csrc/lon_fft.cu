@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_syn_fft(DevTables t, Params 
             for (int base = tid; base < nitems; base += NTHREADS * UN) {
                 double Ec[UN], Es[UN], Oc[UN], Os[UN];
                 double2 ph[UN];
+                int pk[UN], pkc[UN];
                 bool ok[UN];
 #pragma unroll
                 for (int u = 0; u < UN; ++u) {
@@ -187,6 +188,7 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_syn_fft(DevTables t, Params 
                         const double* g = G + (((int64_t)(mlo + mm) * R + row) * 2) * NC + colidx(0, b0 + f, t.GS);
                         Ec[u] = g[0]; Es[u] = g[t.GS]; Oc[u] = g[NC]; Os[u] = g[NC + t.GS];
                         ph[u] = t.phase[mlo + mm];
+                        pk[u] = perm[mm]; pkc[u] = perm[(K - mm) % K];
                     }
                 }
 #pragma unroll
@@ -199,14 +201,13 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_syn_fft(DevTables t, Params 
                     const double2 Wa = make_double2(0.5 * (Z.x - Zp.y), 0.5 * (Z.y + Zp.x));              // (Z + i Z')/2        -> k =  m mod K
                     const double2 Wb = make_double2(0.5 * (Z.x + Zp.y), 0.5 * (-Z.y + Zp.x));             // (conj Z + i conj Z')/2 -> k = -m mod K
                     double2* x = smem2 + (size_t)f * fp.stride;
-                    const int k = mm, kc = (K - mm) % K;
                     if (simple) {
-                        if (k == 0) x[padi(perm[0])] = cadd(Wa, Wb);
-                        else { x[padi(perm[k])] = Wa; x[padi(perm[kc])] = Wb; }
+                        if (mm == 0) x[padi(pk[u])] = cadd(Wa, Wb);
+                        else { x[padi(pk[u])] = Wa; x[padi(pkc[u])] = Wb; }
                     } else if (sub == 0) {
-                        double2* p = &x[padi(perm[k])]; *p = cadd(*p, Wa);
+                        double2* p = &x[padi(pk[u])]; *p = cadd(*p, Wa);
                     } else {
-                        double2* p = &x[padi(perm[kc])]; *p = cadd(*p, Wb);
+                        double2* p = &x[padi(pkc[u])]; *p = cadd(*p, Wb);
                     }
                 }
             }
@@ -225,10 +226,18 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_syn_fft(DevTables t, Params 
     if (b < batch) {
         double* o1 = grid + (int64_t)b * gs_b + (int64_t)i1 * gs_lat;
         double* o2 = grid + (int64_t)b * gs_b + (int64_t)(mirror ? i2 : 0) * gs_lat;
-        for (int j = lt; j < K; j += fp.TPT) {
-            const double2 v = x[padi(j)];
-            o1[(int64_t)j * gs_lon] = v.x;
-            if (mirror) o2[(int64_t)j * gs_lon] = v.y;
+        if (gs_lon == 1 && (K & 1) == 0 && ((reinterpret_cast<uintptr_t>(o1) | reinterpret_cast<uintptr_t>(o2)) & 15) == 0) {
+            for (int j = 2 * lt; j < K; j += 2 * fp.TPT) {          // two longitudes per thread: 16-byte row stores
+                const double2 v0 = x[padi(j)], v1 = x[padi(j + 1)];
+                *reinterpret_cast<double2*>(o1 + j) = make_double2(v0.x, v1.x);
+                if (mirror) *reinterpret_cast<double2*>(o2 + j) = make_double2(v0.y, v1.y);
+            }
+        } else {
+            for (int j = lt; j < K; j += fp.TPT) {
+                const double2 v = x[padi(j)];
+                o1[(int64_t)j * gs_lon] = v.x;
+                if (mirror) o2[(int64_t)j * gs_lon] = v.y;
+            }
         }
     }
 }
@@ -249,10 +258,19 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_ana_fft(DevTables t, Params 
         const bool live = b < batch;
         const double* f1 = grid + (int64_t)b * gs_b + (int64_t)i1 * gs_lat;
         const double* f2 = grid + (int64_t)b * gs_b + (int64_t)(mirror ? i2 : 0) * gs_lat;
-        for (int j = lt; j < K; j += fp.TPT) {
-            double2 v = make_double2(0.0, 0.0);
-            if (live) { v.x = f1[(int64_t)j * gs_lon]; if (mirror) v.y = f2[(int64_t)j * gs_lon]; }
-            x[padi(j)] = v;
+        if (live && gs_lon == 1 && (K & 1) == 0 && ((reinterpret_cast<uintptr_t>(f1) | reinterpret_cast<uintptr_t>(f2)) & 15) == 0) {
+            for (int j = 2 * lt; j < K; j += 2 * fp.TPT) {          // two longitudes per thread: 16-byte row loads
+                const double2 a = *reinterpret_cast<const double2*>(f1 + j);
+                const double2 c = mirror ? *reinterpret_cast<const double2*>(f2 + j) : make_double2(0.0, 0.0);
+                x[padi(j)] = make_double2(a.x, c.x);
+                x[padi(j + 1)] = make_double2(a.y, c.y);
+            }
+        } else {
+            for (int j = lt; j < K; j += fp.TPT) {
+                double2 v = make_double2(0.0, 0.0);
+                if (live) { v.x = f1[(int64_t)j * gs_lon]; if (mirror) v.y = f2[(int64_t)j * gs_lon]; }
+                x[padi(j)] = v;
+            }
         }
     }
     __syncthreads();
