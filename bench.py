@@ -98,7 +98,10 @@ def cpu_sample(steps, warmup, per_step_scale=1.0):
     from oracle import oracle as O
     from shxarray_b200 import synthetic as S
     kind = O.best_kind()
-    nthr = O.max_threads()
+    try:
+        nthr = len(os.sched_getaffinity(0))      # torchrun exports OMP_NUM_THREADS=1: ask for every usable host thread explicitly
+    except AttributeError:
+        nthr = os.cpu_count() or 1
     lon, lat, _ = S.gauss_grid(NLAT, NLON)
     n, m = O.nm_index(NMAX)
     c = S.random_coefficients(NMAX, BATCH, kaula=True)
@@ -113,9 +116,9 @@ def cpu_sample(steps, warmup, per_step_scale=1.0):
     vals, t_syn, t_ana = [], [], []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        O.synthesis(c, n, m, lon[cols_s], lat[rows], grid=True, kind=kind)
+        O.synthesis(c, n, m, lon[cols_s], lat[rows], grid=True, kind=kind, nthreads=nthr)
         t1 = time.perf_counter()
-        O.analysis(f, NMAX, lon[cols_a], lat[rows], kind=kind, weight=w)
+        O.analysis(f, NMAX, lon[cols_a], lat[rows], kind=kind, weight=w, nthreads=nthr)
         t2 = time.perf_counter()
         if it >= warmup:
             full_s = (t1 - t0) * (NLAT * NLON) / (len(rows) * len(cols_s))
@@ -168,6 +171,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
