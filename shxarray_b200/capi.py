@@ -178,6 +178,10 @@ class Plan:
         except Exception:
             pass
 
+    def multiply_dev(self, syn_b, ana, batch, a_ptr, as_b, as_nm, b_ptr, bs_b, bs_nm, out_ptr, os_b, os_nm, stream=0):
+        """self = synthesis plan of operand a; syn_b = synthesis plan of operand b; ana = analysis plan (same grid)."""
+        check(lib().shb200_multiply(self._h, syn_b._h, ana._h, batch, a_ptr, as_b, as_nm, b_ptr, bs_b, bs_nm, out_ptr, os_b, os_nm, stream))
+
     def stage_times(self):
         """dict of per-stage device ms of the last synthesis/analysis (plan needs FLAG_TIMING)."""
         ms = np.zeros(6)

@@ -322,6 +322,39 @@ class SHEngine:
         return out
 
 
+    # ------------------------------------------------------------------------------------------
+    def multiply(self, coef_a, nmax_a, coef_b, nmax_b):
+        """Product of two SH fields through the spatial domain, kept on the device (shtns.py:394-420):
+        Gauss grid of nmax_a+nmax_b, two syntheses, pointwise product, Gauss-quadrature analysis.
+        coef_a [B, (nmax_a+1)^2], coef_b [B, (nmax_b+1)^2] full triangles in nm order; torch CUDA tensors or numpy.
+        Returns [B, (nmax_a+nmax_b+1)^2]."""
+        import torch
+        nmax = int(nmax_a) + int(nmax_b)
+        g = lonlat_grid(nmax, gtype="gauss")
+        lon, lat, lw = g["lon"], g["lat"], g["lat_weights"]
+        host = not _is_torch(coef_a)
+        dev = torch.device("cuda", self.device)
+        ta = torch.as_tensor(np.ascontiguousarray(coef_a), device=dev) if host else coef_a
+        tb = torch.as_tensor(np.ascontiguousarray(coef_b), device=dev) if host else coef_b
+        if ta.ndim == 1:
+            ta, tb = ta[None], tb[None]
+        B = ta.shape[0]
+        na, ma = nm_index(nmax_a)
+        nb_, mb = nm_index(nmax_b)
+        pa = self.get_plan(int(nmax_a), lat, lon, B, n=na, m=ma)
+        pb = pa if nmax_a == nmax_b else self.get_plan(int(nmax_b), lat, lon, B, n=nb_, m=mb)
+        pc = self.get_plan(nmax, lat, lon, B, quadrature=capi.QUAD_LATWEIGHTS, weight=1.0 / (2.0 * len(lon)), lat_weights=lw)
+        out = torch.empty((B, (nmax + 1) ** 2), dtype=torch.float64, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        step = min(pa.max_batch, pb.max_batch, pc.max_batch)
+        for b0 in range(0, B, step):
+            nb = min(step, B - b0)
+            pa.multiply_dev(pb, pc, nb, ta[b0].data_ptr(), ta.stride(0), ta.stride(1), tb[b0].data_ptr(), tb.stride(0), tb.stride(1),
+                            out[b0].data_ptr(), out.stride(0), out.stride(1), stream)
+            self.launches += 2 * pa.info.launches_synthesis + pc.info.launches_analysis + 1
+        return out.cpu().numpy() if host else out
+
+
 _default = {}
 
 
