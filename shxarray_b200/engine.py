@@ -88,9 +88,23 @@ def analysis_weight_shlib(lon, lat):
     return float(abs(stepx * stepy) / (4 * np.pi))
 
 
+_gauss_cache = {}
+
+
 def gauss_lat_weights(lat):
     """Gauss-Legendre weights for a latitude vector that consists of the nlat Gauss nodes (either order)."""
     lat = np.asarray(lat, dtype=np.float64)
+    key = _digest(lat)
+    if key in _gauss_cache:
+        return _gauss_cache[key]
+    w = _gauss_lat_weights(lat)
+    if len(_gauss_cache) > 64:
+        _gauss_cache.clear()
+    _gauss_cache[key] = w
+    return w
+
+
+def _gauss_lat_weights(lat):
     x, w = capi.gauss_nodes(len(lat))
     s = np.sin(np.deg2rad(lat))
     if np.allclose(s, x, rtol=0, atol=1e-10):
@@ -104,15 +118,37 @@ def _is_torch(x):
     return type(x).__module__.startswith("torch")
 
 
+_w64 = {}
+
+
+def _weights64(n):
+    if n not in _w64:
+        if len(_w64) > 16:
+            _w64.clear()
+        _w64[n] = (np.arange(n, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)) | np.uint64(1)
+    return _w64[n]
+
+
 def _digest(*arrays):
+    """Plan-cache key of coordinate / index arrays.  Small arrays: blake2b of the bytes.  Large ones (the nm list of a
+    high-degree field is megabytes): two position-weighted 64-bit checksums, ~1 ms instead of ~15 ms per call."""
     h = hashlib.blake2b(digest_size=16)
     for a in arrays:
         if a is None:
             h.update(b"-")
-        else:
-            a = np.ascontiguousarray(a)
-            h.update(str(a.dtype).encode() + str(a.shape).encode())
+            continue
+        a = np.ascontiguousarray(a)
+        h.update(str(a.dtype).encode() + str(a.shape).encode())
+        if a.nbytes <= 65536:
             h.update(a.tobytes())
+        else:
+            raw = a.reshape(-1).view(np.uint8)
+            n8 = raw.size // 8 * 8
+            h.update(raw[n8:].tobytes())
+            v = raw[:n8].view(np.uint64)
+            w = _weights64(len(v))
+            h.update(int(np.add.reduce(v)).to_bytes(8, "little") + int(np.add.reduce(v * w)).to_bytes(8, "little"))
+            h.update(a.reshape(-1)[:64].tobytes() + a.reshape(-1)[-64:].tobytes())
     return h.hexdigest()
 
 

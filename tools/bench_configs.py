@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""Times the BASELINE.json configs other than the headline one (device-resident, CUDA events) and reports parity of
+the synthesis->analysis round trip where the quadrature is exact.  Not the driver's bench (that is bench.py)."""
+import json
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import shxarray_b200 as sb
+from shxarray_b200 import capi, synthetic as S
+
+
+def timeit(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def run(tag, nmax, B, gtype, quad, flags=0, lon=None, lat=None, lw=None, weight=None):
+    eng = sb.SHEngine(0, flags=flags | capi.FLAG_TIMING)
+    if lon is None:
+        g = sb.lonlat_grid(nmax, gtype=gtype)
+        lon, lat = g["lon"], g["lat"]
+    c = torch.from_numpy(S.random_coefficients(nmax, B, kaula=True)).cuda()
+    f = eng.synthesis(c, lon=lon, lat=lat, nmax=nmax)
+    kw = dict(quadrature=quad)
+    if quad == "weights":
+        kw.update(lat_weights=lw, weight=weight)
+    a = eng.analysis(f, nmax, lon, lat, **kw)
+    t_s = timeit(lambda: eng.synthesis(c, lon=lon, lat=lat, nmax=nmax, out=f))
+    t_a = timeit(lambda: eng.analysis(f, nmax, lon, lat, out=a, **kw))
+    plans = list(eng._plans.values())
+    info = {("ana" if p.info.launches_analysis and p is plans[-1] else "syn"): (p.info.dmma, p.info.lon_fft, p.info.nrows) for p in plans}
+    err = float(((a - c).abs().amax(dim=1) / c.abs().amax(dim=1)).max())
+    res = dict(config=tag, nmax=nmax, batch=B, grid=[len(lat), len(lon)], synthesis_ms=t_s, analysis_ms=t_a,
+               fields_per_s_roundtrip=B / ((t_s + t_a) * 1e-3), roundtrip_rel_err=err, kernels=str(info))
+    print(json.dumps(res), flush=True)
+    eng.clear()
+    return res
+
+
+if __name__ == "__main__":
+    out = []
+    out.append(run("cfg1 nmax60 shlib 1deg B=1", 60, 1, "regular", "shlib"))
+    out.append(run("cfg2 nmax96 0.5deg B=240", 96, 240, "regular", "shlib"))
+    out.append(run("cfg5 nmax256 gauss B=4", 256, 4, "gauss", "gauss"))
+    out.append(run("cfg3 nmax720 gauss B=64", 720, 64, "gauss", "gauss"))
+    d = 1.0 / 12
+    lat = np.arange(-90 + d / 2, 90, d)
+    lon = np.arange(0, 360, d)
+    w = (d * np.pi / 180) ** 2 / (4 * np.pi)
+    out.append(run("cfg4 nmax2160 5min B=1", 2160, 1, None, "weights", lon=lon, lat=lat, lw=np.cos(lat * (np.pi / 180)), weight=w))
+    out.append(run("cfg4b nmax2160 5min B=16 (fused recursion kernels, no P table)", 2160, 16, None, "weights", lon=lon, lat=lat, lw=np.cos(lat * (np.pi / 180)), weight=w))
+    json.dump(out, open("gpurun_out/configs_r01.json", "w"), indent=1)
