@@ -53,7 +53,8 @@ if __name__ == "__main__":
     out.append(run("cfg5 nmax256 gauss B=4", 256, 4, "gauss", "gauss"))
     out.append(run("cfg3 nmax720 gauss B=64", 720, 64, "gauss", "gauss"))
     d = 1.0 / 12
-    lat = np.arange(-90 + d / 2, 90, d)
+    h = np.arange(d / 2, 90, d)
+    lat = np.concatenate([-h[::-1], h])          # bit-exact mirror symmetry (np.arange(-90+d/2, 90, d) is off by ulps for d=1/12)
     lon = np.arange(0, 360, d)
     w = (d * np.pi / 180) ** 2 / (4 * np.pi)
     out.append(run("cfg4 nmax2160 5min B=1", 2160, 1, None, "weights", lon=lon, lat=lat, lw=np.cos(lat * (np.pi / 180)), weight=w))
