@@ -44,6 +44,12 @@ struct DevTables {
     const int64_t* slot_src;  // [tri_size*2] index into the user nm list for (slot, cos/sin) or -1
     int nmax, nrows, nlat, nlon, Bp, NC;
     int GS;               // field-group size of the column order (8, or 4 for tiny batches)
+    int Cs, Gs;           // row strides (doubles) of Cm (NC + 2) and G (NC).  The 2 pad columns of Cm make every row start
+                          // 16 B mod 64 B, so a CONTIGUOUS block of rows lands in shared memory as a bank-conflict-free padded
+                          // tile with a single cp.async.bulk (legendre_tab.cu).  G keeps 128-byte aligned rows: the longitude
+                          // stage touches it in 128-byte groups and lost 20 % when its rows were padded the same way (r01).
+    const int64_t* pt_base;  // [nmax+2] first 16-degree block of each order in the tiled P table
+    int RT32;                // row tiles (of 32) in the P table = Rpad/32
 };
 
 // Column of (cos/sin cs, field b) inside a Cm / G row: fields come in groups of GS with the cosine and sine part of a
@@ -79,9 +85,9 @@ struct Plan {
     DevTables t{};
     // owned device memory
     std::vector<void*> owned;
-    double* Cm = nullptr;   // [tri_size][NC]
-    double* G = nullptr;    // [(nmax+1)][nrows][2][NC]
-    double* Ptab = nullptr; // [tri_size][Rpad] device-resident P_nm table (legendre_tab.cu) or null
+    double* Cm = nullptr;   // [tri_size (+16 slack rows)][Cs]
+    double* G = nullptr;    // [(nmax+1)][nrows][2][Gs] (+64 slack rows)
+    double* Ptab = nullptr; // tiled device-resident P_nm table (legendre_tab.cu) or null
     int Rpad = 0;
     // duplicates in the nm list (rare; Ynm.hpp accepts them, dgemv sums them)
     int64_t ndup = 0;

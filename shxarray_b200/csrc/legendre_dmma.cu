@@ -75,8 +75,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_leg_syn_dmma(DevTables t, const
             const int valid = min(CH, N - m - k0 + 1);
             if (pt == 0) {
                 mbar_expect_tx(&full[s], (uint32_t)(valid * ncols * 8));
-                const double* src = Cm + (tmm + k0) * NC + col0;
-                for (int j = 0; j < valid; ++j) bulk_g2s(&st[s].C[j][0], src + (int64_t)j * NC, (uint32_t)(ncols * 8), &full[s]);
+                const double* src = Cm + (tmm + k0) * t.Cs + col0;
+                for (int j = 0; j < valid; ++j) bulk_g2s(&st[s].C[j][0], src + (int64_t)j * t.Cs, (uint32_t)(ncols * 8), &full[s]);
             }
 #pragma unroll
             for (int j = 0; j < CH; ++j) {
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_leg_syn_dmma(DevTables t, const
                     const int col = col0 + 32 * wc + 8 * cb + 2 * lk;
                     if (col < NC) {
                         double2 v = make_double2(acc[e][g][cb][0], acc[e][g][cb][1]);
-                        *reinterpret_cast<double2*>(G + (((int64_t)m * R + row) * 2 + e) * NC + col) = v;
+                        *reinterpret_cast<double2*>(G + (((int64_t)m * R + row) * 2 + e) * t.Gs + col) = v;
                     }
                 }
         }
@@ -224,8 +224,8 @@ __global__ void __launch_bounds__(ana::NTHREADS, 1) k_leg_ana_dmma(DevTables t, 
                     mbar_wait(&gempty[gb], ((it >> 1) & 1) ^ 1);
                     const int nr = min(RT, R - rt * RT);
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&gfull[gb])), "r"((uint32_t)(nr * 2 * ncols * 8)) : "memory");
-                    const double* src = G + (((int64_t)m * R + rt * RT) * 2) * NC + col0;
-                    for (int j = 0; j < nr * 2; ++j) bulk_g2s(&gt[gb].g[j >> 1][j & 1][0], src + (int64_t)j * NC, (uint32_t)(ncols * 8), &gfull[gb]);
+                    const double* src = G + (((int64_t)m * R + rt * RT) * 2) * t.Gs + col0;
+                    for (int j = 0; j < nr * 2; ++j) bulk_g2s(&gt[gb].g[j >> 1][j & 1][0], src + (int64_t)j * t.Gs, (uint32_t)(ncols * 8), &gfull[gb]);
                 }
                 const double c = t.cost[rr];
                 const double sect = t.sect[(int64_t)m * R + rr];
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(ana::NTHREADS, 1) k_leg_ana_dmma(DevTables t, 
 #pragma unroll
                 for (int cb = 0; cb < 4; ++cb) {
                     const int col = col0 + 32 * cq + 8 * cb + 2 * lk;
-                    if (col < NC) *reinterpret_cast<double2*>(Cm + (tmm + k) * NC + col) = make_double2(acc[nb][cb][0], acc[nb][cb][1]);
+                    if (col < NC) *reinterpret_cast<double2*>(Cm + (tmm + k) * t.Cs + col) = make_double2(acc[nb][cb][0], acc[nb][cb][1]);
                 }
             }
         }

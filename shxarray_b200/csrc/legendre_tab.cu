@@ -7,8 +7,12 @@
 // (ncu r01: consumers wait ~40 % of their time on the "P tile full" barrier).  The normalised P_nm depend
 // only on (nmax, latitudes) -- not on the data -- so the planner generates them ONCE per plan with the same
 // bit-faithful device recursion (k_ptab_gen, one thread per (row, order)) and keeps them in HBM:
-//     Ptab[tri(n,m)][Rpad]   (row fastest, Rpad = rows rounded up to 64, zero padded)
-// 0.8 GB for nmax=720 on 724 latitudes (362 mirror pairs).  Each transform then streams the table once
+//     Ptab[order m][16-degree block][32-row tile][16][34]      (zero padded; 34 = 32 rows + 2 pad doubles)
+// i.e. already in the bank-conflict-free padded layout of the shared-memory tiles, so that ONE cp.async.bulk moves a
+// whole tile (the first version issued one copy per row and the TMA-issuing warp became the bottleneck: ncu r01,
+// consumers 16 % of samples on the "tile full" barrier).  0.87 GB for nmax=720 on 724 latitudes (362 mirror pairs).
+// Cm rows carry 2 pad columns for the same reason (internal.h: Cs); G rows stay 128-byte aligned for the longitude
+// stage and are fetched row by row (64 copies per 32-row tile, against 8 for its P tiles).  Each transform then streams the table once
 // (0.12 ms at HBM speed, overlapped with the contraction) and the kernels below are TMA-fed DMMA GEMMs:
 //   synthesis  G[m][row][E/O][col] = sum_n Ptab[n,m][row] * Cm[n,m][col]      CTA = (m, 64 rows, 128 cols)
 //   analysis   Cm[n,m][col] = sum_row Ptab[n,m][row] * G[m][row][par(n-m)][col] CTA = (m, 128 cols), 128-degree super-blocks
@@ -21,46 +25,44 @@
 
 namespace shb {
 
+constexpr int PT_SUB = 16 * 34;      // doubles per [16 degrees][32 rows + 2] sub-tile
+
 // ------------------------------------------------------------------------------------------------
-// table generation: thread <-> (row, order); writes are coalesced over rows
-__global__ void __launch_bounds__(128) k_ptab_gen(DevTables t, double* __restrict__ Ptab, int Rpad) {
+// table generation: thread <-> (row, order); a warp writes 32 consecutive rows of one sub-tile row (256 B)
+__global__ void __launch_bounds__(128) k_ptab_gen(DevTables t, double* __restrict__ Ptab) {
     const int m = blockIdx.y;
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= Rpad) return;
     const int N = t.nmax, R = t.nrows;
+    if (row >= R) return;                               // pad rows stay zero (memset)
     const int64_t tmm = tri(m, m, N);
-    double* out = Ptab + tmm * Rpad + row;
-    if (row >= R) {
-        for (int k = 0; k <= N - m; ++k) out[(int64_t)k * Rpad] = 0.0;
-        return;
-    }
     LegExact rec;
     rec.init(t.cost[row], t.sect[(int64_t)m * R + row], m);
     const double pmm = t.pmm[(int64_t)m * R + row];
     const double* __restrict__ w = t.wnm + tmm;
     const double* __restrict__ ri = t.rinv + tmm;
-    for (int k = 0; k <= N - m; ++k) out[(int64_t)k * Rpad] = rec.next(w, ri, pmm);
+    double* base = Ptab + (t.pt_base[m] * t.RT32 + (row >> 5)) * PT_SUB + (row & 31);
+    for (int k = 0; k <= N - m; ++k) base[(int64_t)(k >> 4) * t.RT32 * PT_SUB + (k & 15) * 34] = rec.next(w, ri, pmm);
 }
 
 void launch_ptab_gen(const Plan& p, cudaStream_t st) {
-    dim3 grid((p.Rpad + 127) / 128, p.nmax + 1);
-    k_ptab_gen<<<grid, 128, 0, st>>>(p.t, p.Ptab, p.Rpad);
+    dim3 grid((p.nrows + 127) / 128, p.nmax + 1);
+    k_ptab_gen<<<grid, 128, 0, st>>>(p.t, p.Ptab);
 }
 
 // ------------------------------------------------------------------------------------------------
 namespace ts {
 constexpr int TR = 64, CH = 16, NCOLS = 128;
-constexpr int PROW = TR + 2, CROW = NCOLS + 2;
+constexpr int CROW = NCOLS + 2;
 constexpr int STAGES = 8;
 constexpr int NCONS = 256, NTHREADS = NCONS + 32;
 struct __align__(16) Stage {
-    double P[CH][PROW];
-    double C[CH][CROW];
+    double P[2 * PT_SUB];        // two 32-row sub-tiles [16][34]
+    double C[CH * CROW];         // [16][crow], crow = Cs (single column tile, one bulk copy) or 130 (row copies)
 };
 constexpr size_t SMEM = sizeof(Stage) * STAGES + 2 * STAGES * sizeof(uint64_t);
 }  // namespace ts
 
-__global__ void __launch_bounds__(ts::NTHREADS, 1) k_leg_syn_tab(DevTables t, const double* __restrict__ Ptab, int Rpad, const double* __restrict__ Cm,
+__global__ void __launch_bounds__(ts::NTHREADS, 1) k_leg_syn_tab(DevTables t, const double* __restrict__ Ptab, const double* __restrict__ Cm,
                                                                   double* __restrict__ G) {
     using namespace ts;
     extern __shared__ __align__(128) unsigned char smraw[];
@@ -73,27 +75,41 @@ __global__ void __launch_bounds__(ts::NTHREADS, 1) k_leg_syn_tab(DevTables t, co
     const int ncols = min(NCOLS, NC - col0);
     const int nchunks = (N - m + CH) / CH;
     const int64_t tmm = tri(m, m, N);
+    const bool onecopy = NC <= NCOLS;                  // whole rows of Cm fit the tile: contiguous block, padded stride Cs
+    const int crow = onecopy ? t.Cs : CROW;
 
-    // no zero fill of the ring: fragments of degrees beyond nmax are masked in the consumers (0 x stale NaN would poison)
+    // no zero fill: degrees beyond nmax have P = 0 in the table and the Cm rows fetched with them are finite
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCONS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (!onecopy) {      // pad columns / rows of a partial column tile are never written by the row copies
+        for (int i = tid; i < (int)(sizeof(Stage) * STAGES / 8); i += NTHREADS) reinterpret_cast<double*>(smraw)[i] = 0.0;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     __syncthreads();
 
     if (warp == NCONS / 32) {
-        // ------------------------------------------------------------------ TMA warp: lane j streams row j of every stage
+        // ------------------------------------------------------------------ TMA warp
+        const double* psrc = Ptab + (t.pt_base[m] * t.RT32 + 2 * blockIdx.x) * PT_SUB;
         for (int ch = 0; ch < nchunks; ++ch) {
             const int s = ch % STAGES;
             mbar_wait(&empty[s], ((ch / STAGES) & 1) ^ 1);
             const int k0 = ch * CH;
-            const int valid = min(CH, N - m - k0 + 1);
-            if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)(valid * (ncols + TR) * 8));
-            __syncwarp();
-            if (lane < valid) {
-                bulk_g2s(&st[s].C[lane][0], Cm + (tmm + k0 + lane) * NC + col0, (uint32_t)(ncols * 8), &full[s]);
-                bulk_g2s(&st[s].P[lane][0], Ptab + (tmm + k0 + lane) * Rpad + row0, (uint32_t)(TR * 8), &full[s]);
+            if (onecopy) {
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&full[s], (uint32_t)((2 * PT_SUB + CH * crow) * 8));
+                    bulk_g2s(&st[s].P[0], psrc + (int64_t)ch * t.RT32 * PT_SUB, 2 * PT_SUB * 8, &full[s]);
+                    bulk_g2s(&st[s].C[0], Cm + (tmm + k0) * t.Cs, (uint32_t)(CH * crow * 8), &full[s]);
+                }
+            } else {
+                const int valid = min(CH, N - m - k0 + 1);
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&full[s], (uint32_t)(2 * PT_SUB * 8 + valid * ncols * 8));
+                    bulk_g2s(&st[s].P[0], psrc + (int64_t)ch * t.RT32 * PT_SUB, 2 * PT_SUB * 8, &full[s]);
+                }
+                __syncwarp();
+                if (lane < valid) bulk_g2s(&st[s].C[lane * crow], Cm + (tmm + k0 + lane) * t.Cs + col0, (uint32_t)(ncols * 8), &full[s]);
             }
         }
     } else {
@@ -110,8 +126,8 @@ __global__ void __launch_bounds__(ts::NTHREADS, 1) k_leg_syn_tab(DevTables t, co
         for (int ch = 0; ch < nchunks; ++ch) {
             const int s = ch % STAGES;
             mbar_wait(&full[s], (ch / STAGES) & 1);
-            const Stage& S = st[s];
-            const int valid = min(CH, N - m - ch * CH + 1);
+            const double* __restrict__ SP = st[s].P + wr * PT_SUB + lr;
+            const double* __restrict__ SC = st[s].C + 32 * wc + lr;
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
@@ -119,9 +135,9 @@ __global__ void __launch_bounds__(ts::NTHREADS, 1) k_leg_syn_tab(DevTables t, co
                     const int j = 8 * ks + 2 * lk + e;
                     double A[4], B[4];
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) A[g] = j < valid ? S.P[j][32 * wr + 8 * g + lr] : 0.0;   // rows beyond nmax hold stale data
+                    for (int g = 0; g < 4; ++g) A[g] = SP[j * 34 + 8 * g];
 #pragma unroll
-                    for (int cb = 0; cb < 4; ++cb) B[cb] = j < valid ? S.C[j][32 * wc + 8 * cb + lr] : 0.0;
+                    for (int cb = 0; cb < 4; ++cb) B[cb] = SC[j * crow + 8 * cb];
 #pragma unroll
                     for (int g = 0; g < 4; ++g)
 #pragma unroll
@@ -139,7 +155,7 @@ __global__ void __launch_bounds__(ts::NTHREADS, 1) k_leg_syn_tab(DevTables t, co
 #pragma unroll
                 for (int cb = 0; cb < 4; ++cb) {
                     const int col = col0 + 32 * wc + 8 * cb + 2 * lk;
-                    if (col < NC) *reinterpret_cast<double2*>(G + (((int64_t)m * R + row) * 2 + e) * NC + col) = make_double2(acc[e][g][cb][0], acc[e][g][cb][1]);
+                    if (col < NC) *reinterpret_cast<double2*>(G + (((int64_t)m * R + row) * 2 + e) * t.Gs + col) = make_double2(acc[e][g][cb][0], acc[e][g][cb][1]);
                 }
         }
     }
@@ -148,15 +164,15 @@ __global__ void __launch_bounds__(ts::NTHREADS, 1) k_leg_syn_tab(DevTables t, co
 // ------------------------------------------------------------------------------------------------
 namespace ta {
 constexpr int RT = 32, NS = 32, SB = 128, NCOLS = 128;
-constexpr int PROW = RT + 2, CROW = NCOLS + 2;
+constexpr int CROW = NCOLS + 2;
 constexpr int PSTAGES = 8;
 constexpr int NCONS = 256, NTHREADS = NCONS + 32;
-struct __align__(16) GTile { double g[RT][2][CROW]; };
-struct __align__(16) PTile { double p[NS][PROW]; };
+struct __align__(16) GTile { double g[RT * 2 * CROW]; };     // [32 rows][E/O][grow]
+struct __align__(16) PTile { double p[2 * PT_SUB]; };        // two 16-degree sub-tiles [16][34]
 constexpr size_t SMEM = sizeof(GTile) * 2 + sizeof(PTile) * PSTAGES + sizeof(uint64_t) * (2 * PSTAGES + 4);
 }  // namespace ta
 
-__global__ void __launch_bounds__(ta::NTHREADS, 1) k_leg_ana_tab(DevTables t, const double* __restrict__ Ptab, int Rpad, const double* __restrict__ G,
+__global__ void __launch_bounds__(ta::NTHREADS, 1) k_leg_ana_tab(DevTables t, const double* __restrict__ Ptab, const double* __restrict__ G,
                                                                   double* __restrict__ Cm) {
     using namespace ta;
     extern __shared__ __align__(128) unsigned char smraw[];
@@ -173,41 +189,45 @@ __global__ void __launch_bounds__(ta::NTHREADS, 1) k_leg_ana_tab(DevTables t, co
     const int nsb = (N - m + SB) / SB;
     const int nrt = (R + RT - 1) / RT;
     const int64_t tmm = tri(m, m, N);
+    constexpr int grow = CROW;
 
-    // no zero fill: rows beyond the last latitude row and degrees beyond nmax are masked in the consumers
     if (tid == 0) {
         for (int s = 0; s < PSTAGES; ++s) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], NCONS / 32); }
         for (int g = 0; g < 2; ++g) { mbar_init(&gfull[g], 1); mbar_init(&gempty[g], NCONS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
     if (warp == NCONS / 32) {
         // ------------------------------------------------------------------ TMA warp
+        const double* pbase = Ptab + t.pt_base[m] * t.RT32 * PT_SUB;
         int sidx = 0;
         for (int sb = 0; sb < nsb; ++sb) {
             const int ninner = min(SB / NS, (N - m - sb * SB + NS) / NS);     // stages of this super-block that hold degrees <= nmax
             for (int rt = 0; rt < nrt; ++rt) {
                 const int it = sb * nrt + rt;
                 const int gb = it & 1;
-                const int nr = min(RT, R - rt * RT);
                 mbar_wait(&gempty[gb], ((it >> 1) & 1) ^ 1);
-                if (lane == 0) mbar_arrive_expect_tx(&gfull[gb], (uint32_t)(nr * 2 * ncols * 8));
-                __syncwarp();
-                if (lane < nr) {
-                    const double* src = G + (((int64_t)m * R + rt * RT + lane) * 2) * NC + col0;
-                    bulk_g2s(&gt[gb].g[lane][0][0], src, (uint32_t)(ncols * 8), &gfull[gb]);
-                    bulk_g2s(&gt[gb].g[lane][1][0], src + NC, (uint32_t)(ncols * 8), &gfull[gb]);
+                {
+                    const int nr = min(RT, R - rt * RT);
+                    if (lane == 0) mbar_arrive_expect_tx(&gfull[gb], (uint32_t)(nr * 2 * ncols * 8));
+                    __syncwarp();
+                    if (lane < nr) {
+                        const double* src = G + (((int64_t)m * R + rt * RT + lane) * 2) * t.Gs + col0;
+                        bulk_g2s(&gt[gb].g[(lane * 2 + 0) * grow], src, (uint32_t)(ncols * 8), &gfull[gb]);
+                        bulk_g2s(&gt[gb].g[(lane * 2 + 1) * grow], src + t.Gs, (uint32_t)(ncols * 8), &gfull[gb]);
+                    }
                 }
                 for (int inner = 0; inner < ninner; ++inner, ++sidx) {
                     const int s = sidx % PSTAGES;
                     mbar_wait(&pempty[s], ((sidx / PSTAGES) & 1) ^ 1);
                     const int k0 = sb * SB + inner * NS;
-                    const int valid = min(NS, N - m - k0 + 1);
-                    if (lane == 0) mbar_arrive_expect_tx(&pfull[s], (uint32_t)(valid * RT * 8));
-                    __syncwarp();
-                    if (lane < valid) bulk_g2s(&ptile[s].p[lane][0], Ptab + (tmm + k0 + lane) * Rpad + rt * RT, (uint32_t)(RT * 8), &pfull[s]);
+                    const int nblk = (N - m - k0 + 1) > 16 ? 2 : 1;                 // 16-degree blocks of this stage that exist
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(&pfull[s], (uint32_t)(nblk * PT_SUB * 8));
+                        for (int q = 0; q < nblk; ++q)
+                            bulk_g2s(&ptile[s].p[q * PT_SUB], pbase + ((int64_t)(k0 / 16 + q) * t.RT32 + rt) * PT_SUB, PT_SUB * 8, &pfull[s]);
+                    }
                 }
             }
         }
@@ -228,26 +248,24 @@ __global__ void __launch_bounds__(ta::NTHREADS, 1) k_leg_ana_tab(DevTables t, co
                 const int gb = it & 1;
                 const int nr = min(RT, R - rt * RT);
                 mbar_wait(&gfull[gb], (it >> 1) & 1);
-                const GTile& GT = gt[gb];
+                const double* __restrict__ GT = gt[gb].g + e * grow + 32 * cq + lr;
 #pragma unroll
                 for (int inner = 0; inner < SB / NS; ++inner) {
                     if (inner >= ninner) break;
                     const int s = sidx % PSTAGES;
                     mbar_wait(&pfull[s], (sidx / PSTAGES) & 1);
                     ++sidx;
-                    const PTile& PT = ptile[s];
-                    const int valid = N - m - (sb * SB + inner * NS) + 1;     // degrees of this stage that exist
+                    const double* __restrict__ PT = ptile[s].p + (2 * lr + e) * 34 + lk;
+                    const bool two = (N - m - (sb * SB + inner * NS) + 1) > 16;     // second 16-degree block present
 #pragma unroll
                     for (int ks = 0; ks < RT / 4; ++ks) {
                         double A[2], B[4];
+                        A[0] = PT[4 * ks];
+                        A[1] = two ? PT[PT_SUB + 4 * ks] : 0.0;
 #pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            const int j = 16 * q + 2 * lr + e;
-                            A[q] = j < valid ? PT.p[j][4 * ks + lk] : 0.0;
-                        }
-                        const bool rowok = 4 * ks + lk < nr;
+                        const bool rowok = 4 * ks + lk < nr;        // rows past the last latitude were never copied
 #pragma unroll
-                        for (int cb = 0; cb < 4; ++cb) B[cb] = rowok ? GT.g[4 * ks + lk][e][32 * cq + 8 * cb + lr] : 0.0;
+                        for (int cb = 0; cb < 4; ++cb) B[cb] = rowok ? GT[(4 * ks + lk) * 2 * grow + 8 * cb] : 0.0;
 #pragma unroll
                         for (int q = 0; q < 2; ++q)
 #pragma unroll
@@ -265,7 +283,7 @@ __global__ void __launch_bounds__(ta::NTHREADS, 1) k_leg_ana_tab(DevTables t, co
 #pragma unroll
                 for (int cb = 0; cb < 4; ++cb) {
                     const int col = col0 + 32 * cq + 8 * cb + 2 * lk;
-                    if (col < NC) *reinterpret_cast<double2*>(Cm + (tmm + k) * NC + col) = make_double2(acc[nb][cb][0], acc[nb][cb][1]);
+                    if (col < NC) *reinterpret_cast<double2*>(Cm + (tmm + k) * t.Cs + col) = make_double2(acc[nb][cb][0], acc[nb][cb][1]);
                 }
             }
         }
@@ -280,7 +298,7 @@ bool launch_legendre_syn_tab(const Plan& p, cudaStream_t st) {
         attr = true;
     }
     dim3 grid((p.nrows + ts::TR - 1) / ts::TR, p.nmax + 1, (p.NC + ts::NCOLS - 1) / ts::NCOLS);
-    k_leg_syn_tab<<<grid, ts::NTHREADS, ts::SMEM, st>>>(p.t, p.Ptab, p.Rpad, p.Cm, p.G);
+    k_leg_syn_tab<<<grid, ts::NTHREADS, ts::SMEM, st>>>(p.t, p.Ptab, p.Cm, p.G);
     return true;
 }
 
@@ -292,7 +310,7 @@ bool launch_legendre_ana_tab(const Plan& p, cudaStream_t st) {
         attr = true;
     }
     dim3 grid(p.nmax + 1, (p.NC + ta::NCOLS - 1) / ta::NCOLS);
-    k_leg_ana_tab<<<grid, ta::NTHREADS, ta::SMEM, st>>>(p.t, p.Ptab, p.Rpad, p.G, p.Cm);
+    k_leg_ana_tab<<<grid, ta::NTHREADS, ta::SMEM, st>>>(p.t, p.Ptab, p.G, p.Cm);
     return true;
 }
 

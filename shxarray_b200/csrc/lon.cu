@@ -29,9 +29,9 @@ __global__ void __launch_bounds__(128) k_lon_syn_dense(DevTables t, int batch, i
         for (int m = 0; m <= N; ++m) {
             double sn, cs;
             sincos((double)m * lonr, &sn, &cs);   // Ynm.hpp:127
-            const double* g = G + (((int64_t)m * R + row) * 2) * NC;
+            const double* g = G + (((int64_t)m * R + row) * 2) * t.Gs;
             const int cc = colidx(0, b, t.GS), sc = colidx(1, b, t.GS);
-            double Ec = g[cc], Es = g[sc], Oc = g[NC + cc], Os = g[NC + sc];
+            double Ec = g[cc], Es = g[sc], Oc = g[t.Gs + cc], Os = g[t.Gs + sc];
             s1 += (Ec + Oc) * cs + (Es + Os) * sn;
             s2 += (Ec - Oc) * cs + (Es - Os) * sn;
         }
@@ -63,9 +63,9 @@ __global__ void __launch_bounds__(128) k_lon_ana_dense(DevTables t, int batch, c
             }
             a *= w1; bb *= w1; ap *= w2; bp *= w2;
         }
-        double* g = G + (((int64_t)m * R + row) * 2) * NC;
+        double* g = G + (((int64_t)m * R + row) * 2) * t.Gs;
         const int cc = colidx(0, b, t.GS), sc = colidx(1, b, t.GS);
-        g[cc] = a + ap; g[sc] = bb + bp; g[NC + cc] = a - ap; g[NC + sc] = bb - bp;
+        g[cc] = a + ap; g[sc] = bb + bp; g[t.Gs + cc] = a - ap; g[t.Gs + sc] = bb - bp;
     }
 }
 

@@ -185,8 +185,8 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_syn_fft(DevTables t, Params 
                     const int mm = idx / NF, f = idx - mm * NF;
                     ok[u] = idx < nitems && b0 + f < batch;
                     if (ok[u]) {
-                        const double* g = G + (((int64_t)(mlo + mm) * R + row) * 2) * NC + colidx(0, b0 + f, t.GS);
-                        Ec[u] = g[0]; Es[u] = g[t.GS]; Oc[u] = g[NC]; Os[u] = g[NC + t.GS];
+                        const double* g = G + (((int64_t)(mlo + mm) * R + row) * 2) * t.Gs + colidx(0, b0 + f, t.GS);
+                        Ec[u] = g[0]; Es[u] = g[t.GS]; Oc[u] = g[t.Gs]; Os[u] = g[t.Gs + t.GS];
                         ph[u] = t.phase[mlo + mm];
                         pk[u] = perm[mm]; pkc[u] = perm[(K - mm) % K];
                     }
@@ -291,10 +291,10 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_ana_fft(DevTables t, Params 
         const double2 phc = cconj(t.phase[m]);
         const double2 Z = cmul(F, phc), Zp = cmul(Fp, phc);                            // a_m - i b_m
         const double a = w1 * Z.x, bb = -w1 * Z.y, ap = w2 * Zp.x, bp = -w2 * Zp.y;
-        double* g = G + (((int64_t)m * R + row) * 2) * NC + colidx(0, b, t.GS);
+        double* g = G + (((int64_t)m * R + row) * 2) * t.Gs + colidx(0, b, t.GS);
         const bool live = b < batch;
         g[0] = live ? a + ap : 0.0; g[t.GS] = live ? bb + bp : 0.0;
-        g[NC] = live ? a - ap : 0.0; g[NC + t.GS] = live ? bb - bp : 0.0;
+        g[t.Gs] = live ? a - ap : 0.0; g[t.Gs + t.GS] = live ? bb - bp : 0.0;
     }
 }
 

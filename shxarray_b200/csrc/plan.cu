@@ -244,23 +244,33 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
     if ((rc = upload(p, dup_src, &p.dup_src))) return rc;
     if ((rc = upload(p, fwd, &p.fwd_slot))) return rc;
     t.nmax = N; t.nrows = R; t.nlat = d.nlat; t.nlon = d.nlon; t.Bp = p.Bp; t.NC = p.NC; t.GS = p.Bp >= 8 ? 8 : 4;
+    t.Cs = p.NC + 2; t.Gs = p.NC; t.pt_base = nullptr; t.RT32 = 0;
 
     void* ptr;
-    if ((rc = dev_alloc(p, sizeof(double) * (size_t)T * p.NC, &ptr))) return rc;
+    // 16 / 64 slack rows: the tensor-core kernels fetch whole 16-degree / 32-row blocks, also past the last order
+    const size_t cm_elems = ((size_t)T + 16) * t.Cs, g_elems = ((size_t)(N + 1) * R * 2 + 64) * t.Gs;
+    if ((rc = dev_alloc(p, sizeof(double) * cm_elems, &ptr))) return rc;
     p.Cm = (double*)ptr;
-    if ((rc = dev_alloc(p, sizeof(double) * (size_t)(N + 1) * R * 2 * p.NC, &ptr))) return rc;
+    if ((rc = dev_alloc(p, sizeof(double) * g_elems, &ptr))) return rc;
     p.G = (double*)ptr;
-    SHB_CUDA(cudaMemset(p.Cm, 0, sizeof(double) * (size_t)T * p.NC));
-    SHB_CUDA(cudaMemset(p.G, 0, sizeof(double) * (size_t)(N + 1) * R * 2 * p.NC));
+    SHB_CUDA(cudaMemset(p.Cm, 0, sizeof(double) * cm_elems));
+    SHB_CUDA(cudaMemset(p.G, 0, sizeof(double) * g_elems));
     SHB_CUDA(cudaStreamCreateWithFlags(&p.own_stream, cudaStreamNonBlocking));
     // device-resident P_nm table for the tensor-core kernels (legendre_tab.cu) when it fits the budget
     if (p.dmma && !(d.flags & SHB200_FLAG_NO_PTABLE) && p.NC >= 32 && d.mode == SHB200_MODE_GRID) {
         p.Rpad = (R + 63) / 64 * 64;
+        // tiled layout: [order][16-degree block][32-row tile][16][34] doubles (legendre_tab.cu)
+        std::vector<int64_t> ptb(N + 2, 0);
+        for (int m = 0; m <= N; ++m) ptb[m + 1] = ptb[m] + (N - m + 16) / 16;
+        const size_t pt_elems = (size_t)ptb[N + 1] * (p.Rpad / 32) * (16 * 34);
         const double budget_mib = d.ptable_budget_mib > 0 ? (double)d.ptable_budget_mib : 6144.0;
-        const double need_mib = (double)T * p.Rpad * 8.0 / (1024.0 * 1024.0);
+        const double need_mib = (double)pt_elems * 8.0 / (1024.0 * 1024.0);
         if (need_mib <= budget_mib) {
-            if ((rc = dev_alloc(p, sizeof(double) * (size_t)T * p.Rpad, &ptr))) return rc;
+            if ((rc = upload(p, ptb, &t.pt_base))) return rc;
+            t.RT32 = p.Rpad / 32;
+            if ((rc = dev_alloc(p, sizeof(double) * pt_elems, &ptr))) return rc;
             p.Ptab = (double*)ptr;
+            SHB_CUDA(cudaMemset(p.Ptab, 0, sizeof(double) * pt_elems));
             launch_ptab_gen(p, 0);
             SHB_CUDA(cudaDeviceSynchronize());
         }
