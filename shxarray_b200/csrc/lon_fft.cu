@@ -29,6 +29,8 @@ struct Params {
 };
 
 __device__ __forceinline__ int padi(int i) { return i + (i >> 3); }
+// barrier among the `count` threads that work on one transform (ids 1..15; id 0 is __syncthreads)
+__device__ __forceinline__ void group_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
@@ -217,9 +219,11 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_syn_fft(DevTables t, Params 
     // ---- inverse FFT (decimation in time)
     const int tr = tid / fp.TPT, lt = tid - tr * fp.TPT;
     double2* x = smem2 + (size_t)tr * fp.stride;
+    // the transforms of a CTA are independent from here on: per-transform named barriers let their passes and row
+    // stores drift apart and overlap instead of marching in lock step
     for (int s = 0; s < fp.nrad; ++s) {
         run_pass<true>(fp.rad[s], x, K, fp.ns[s], fp.TPT, lt, t.tw, +1.0);
-        __syncthreads();
+        group_sync(1 + tr, fp.TPT);
     }
     // ---- store: real part -> primary latitude, imaginary part -> mirror latitude
     const int b = b0 + tr;
@@ -273,11 +277,12 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_ana_fft(DevTables t, Params 
             }
         }
     }
-    __syncthreads();
+    group_sync(1 + tr, fp.TPT);
     for (int s = fp.nrad - 1; s >= 0; --s) {
         run_pass<false>(fp.rad[s], x, K, fp.ns[s], fp.TPT, lt, t.tw, -1.0);
-        __syncthreads();
+        if (s > 0) group_sync(1 + tr, fp.TPT);
     }
+    __syncthreads();
     for (int idx = tid; idx < (N + 1) * NF; idx += NTHREADS) {
         const int m = idx / NF, f = idx - m * NF;
         const int b = b0 + f;
