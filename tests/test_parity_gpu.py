@@ -251,10 +251,12 @@ def test_edge_cases(engine):
         engine.analysis(np.zeros((1, 6, 5)), 3, lon, lat, quadrature="shlib")
 
 
-@pytest.mark.parametrize("nmax,B,gtype", [(720, 64, "gauss"), (96, 240, "regular"), (2160, 16, "regular_lon0")])
-def test_dmma_kernels_match_bitfaithful_dfma_kernels(engine, nmax, B, gtype):
-    """The tensor-core kernels use the division-free recursion; the DFMA kernels are bit-faithful to the reference's
-    P_nm (test_device_recursion_bit_exact) and are oracle-checked above.  At BASELINE batch sizes the two must agree
+@pytest.mark.parametrize("nmax,B,gtype,extra", [(720, 64, "gauss", 0), (96, 240, "regular", 0), (2160, 16, "regular_lon0", 0),
+                                                (360, 40, "regular", capi.FLAG_NO_PTABLE), (96, 100, "regular_lon0", capi.FLAG_NO_PTABLE)])
+def test_dmma_kernels_match_bitfaithful_dfma_kernels(engine, nmax, B, gtype, extra):
+    """The DFMA kernels are bit-faithful to the reference's P_nm (test_device_recursion_bit_exact) and are oracle-checked
+    above.  At BASELINE batch sizes the tensor-core kernels -- P-table fed (extra=0) and with the fused on-the-fly
+    recursion (FLAG_NO_PTABLE, also what runs when the table exceeds its budget, e.g. nmax=2160) -- must agree with them
     to the parity tolerance, in both directions, for white (worst-case) and Kaula spectra."""
     import torch
     if gtype == "regular_lon0" and nmax == 2160:
@@ -265,7 +267,7 @@ def test_dmma_kernels_match_bitfaithful_dfma_kernels(engine, nmax, B, gtype):
     lon, lat = grid["lon"], grid["lat"]
     c = np.concatenate([S.random_coefficients(nmax, B // 2, kaula=False), S.random_coefficients(nmax, B - B // 2, kaula=True, seed=3)])
     ct = torch.from_numpy(c).cuda()
-    f_t = engine.synthesis(ct, lon=lon, lat=lat, nmax=nmax, flags=0)
+    f_t = engine.synthesis(ct, lon=lon, lat=lat, nmax=nmax, flags=extra)
     f_d = engine.synthesis(ct, lon=lon, lat=lat, nmax=nmax, flags=capi.FLAG_NO_DMMA)
     num = (f_t - f_d).abs().amax(dim=(1, 2))
     den = f_d.abs().amax(dim=(1, 2))
@@ -276,7 +278,7 @@ def test_dmma_kernels_match_bitfaithful_dfma_kernels(engine, nmax, B, gtype):
         quad = dict(quadrature="weights", weight=(d * np.pi / 180) ** 2 / (4 * np.pi), lat_weights=np.cos(lat * (np.pi / 180)))
     else:
         quad = dict(quadrature="shlib")
-    a_t = engine.analysis(f_d, nmax, lon, lat, flags=0, **quad)
+    a_t = engine.analysis(f_d, nmax, lon, lat, flags=extra, **quad)
     a_d = engine.analysis(f_d, nmax, lon, lat, flags=capi.FLAG_NO_DMMA, **quad)
     num = (a_t - a_d).abs().amax(dim=1)
     den = a_d.abs().amax(dim=1)
@@ -304,3 +306,45 @@ def test_multiply_roundtrip_pattern(engine):
     two = np.zeros((1, (n2 + 1) ** 2)); two[0, 0] = 3.0
     p = engine.multiply(one, n1, two, n2)
     assert abs(p[0, 0] - 6.0) < 1e-13 and np.abs(p[0, 1:]).max() < 1e-13
+
+
+@pytest.mark.parametrize("flags", [0, capi.FLAG_NO_DMMA])
+def test_aliased_longitudes_and_odd_rows(engine, flags):
+    """Fewer longitudes than 2*nmax+1 (orders alias onto each other exactly as cos(m*lon_j) does on the grid, which shlib
+    evaluates point by point), an equator row (unpaired) and both poles; FFT lengths with factors 3 and 5."""
+    nmax, B = 40, 5
+    n, m = sb.nm_index(nmax)
+    c = S.random_coefficients(nmax, B, kaula=False, seed=9)
+    for lon, lat in ((np.arange(48) * 7.5, np.arange(-90.0, 90.1, 10.0)),            # K=48 < 81, equator + poles
+                     (np.arange(-180.0, 180.0, 12.0), np.arange(-85.0, 86.0, 17.0)),  # K=30 = 2*3*5, lon0 = -180
+                     (np.arange(20) * 18.0 + 3.0, np.array([-30.0, 12.5, 30.0]))):    # K=20, offset start, one mirror pair + a single
+        ref = np.moveaxis(O.synthesis(c, n, m, lon, lat, kind="port"), 2, 0)
+        out = engine.synthesis(c, n, m, lon, lat, flags=flags)
+        assert per_field_err(out, ref) <= TOL
+    # analysis on an aliasing grid: midpoint weights, uniform steps
+    lon = np.arange(0.0, 360.0, 12.0)
+    lat = np.arange(-87.0, 88.0, 6.0)
+    f = np.random.default_rng(4).standard_normal((B, len(lat), len(lon)))
+    ref = O.analysis(f, nmax, lon, lat, kind="port")
+    out = engine.analysis(f, nmax, lon, lat, quadrature="shlib", flags=flags)
+    assert per_field_err(out, ref) <= TOL
+
+
+def test_descending_and_shuffled_latitudes(engine):
+    """shlib does not care about the order of the latitude vector (synthesis.pyx:179 loops over whatever it is given)."""
+    nmax, B = 30, 2
+    n, m = sb.nm_index(nmax)
+    c = S.random_coefficients(nmax, B, kaula=False, seed=10)
+    lon = np.arange(0.0, 360.0, 5.0)
+    lat = np.arange(87.5, -90.0, -5.0)
+    ref = np.moveaxis(O.synthesis(c, n, m, lon, lat, kind="port"), 2, 0)
+    out = engine.synthesis(c, n, m, lon, lat)
+    assert per_field_err(out, ref) <= TOL
+    perm = np.random.default_rng(0).permutation(len(lat))
+    out2 = engine.synthesis(c, n, m, lon, lat[perm])
+    # which row of a mirror pair carries the recursion depends on the order, so equality holds to rounding only
+    assert np.abs(out2 - out[:, perm]).max() <= 1e-13 * np.abs(out).max()
+    f = np.random.default_rng(5).standard_normal((B, len(lat), len(lon)))
+    aref = O.analysis(f, nmax, lon, lat, kind="port")
+    aout = engine.analysis(f, nmax, lon, lat, quadrature="shlib")
+    assert per_field_err(aout, aref) <= TOL
