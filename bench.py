@@ -48,7 +48,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -79,6 +79,15 @@ class ClockSampler:
                     if val.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smmax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed ncu --set full capture."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["kernels"][kernel]
+        return d["dram_bytes_read"] + d["dram_bytes_write"]
+    except Exception:
+        return None
 
 
 def fp64_peak_tflops():
@@ -147,7 +156,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -236,8 +245,9 @@ def main():
     dom = "syn_legendre" if acc["syn_legendre"] >= acc["ana_legendre"] else "ana_legendre"
     peak, peak_src = fp64_peak_tflops()
     achieved = flops_leg / (acc[dom] * 1e-3) * 1e-12
+    kname = {"syn_legendre": "k_leg_syn_tab", "ana_legendre": "k_leg_ana_tab"}[dom] if plan.info.dmma == 2 else None
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "flops_per_launch": flops_leg, "ms_per_launch": acc[dom], "peak_source": peak_src,
+                "traffic": ncu_traffic(kname) if kname else None, "traffic_unit": "bytes per launch (dram read+write, ncu)", "flops_per_launch": flops_leg, "ms_per_launch": acc[dom], "peak_source": peak_src,
                 "symmetry": "mirror-latitude pairing used: F_sym = nsh*L per field" if paired else "no pairing: F_alg = 2*nsh*L per field",
                 "stages_ms": acc}
 
