@@ -110,13 +110,15 @@ template <int R, bool DIT>
 __device__ __forceinline__ void pass(double2* __restrict__ x, int K, int Ns, int tpt, int lt, const double2* __restrict__ tw, double sgn) {
     constexpr int UB = R >= 8 ? 3 : 4;
     const int M = Ns * R, nb = K / R, tws = K / M;
+    const bool pow2 = (Ns & (Ns - 1)) == 0;            // true for all passes before the first radix 3/5
+    const int sh = 31 - __clz(Ns);
     for (int i0 = lt; i0 < nb; i0 += tpt * UB) {
         double2 w1[UB];
         int base[UB], kk[UB];
 #pragma unroll
         for (int u = 0; u < UB; ++u) {
             const int idx = i0 + u * tpt;
-            const int g = idx / Ns, k = idx - g * Ns;
+            const int g = pow2 ? idx >> sh : idx / Ns, k = idx - g * Ns;
             base[u] = idx < nb ? g * M + k : -1;
             kk[u] = k;
             w1[u] = (idx < nb && k > 0) ? tw[k * tws] : make_double2(1.0, 0.0);
@@ -166,50 +168,63 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_syn_fft(DevTables t, Params 
     const int tid = threadIdx.x, NTHREADS = blockDim.x;
     const int i1 = t.row_i1[row], i2 = t.row_i2[row];
     const bool mirror = i2 >= 0;
-    for (int i = tid; i < NF * fp.stride; i += NTHREADS) smem2[i] = make_double2(0.0, 0.0);
-    __syncthreads();
-    // ---- spectrum assembly: thread <-> (order m, field), fields fastest
-    const bool simple = 2 * N < K;
+    // ---- spectrum assembly: thread <-> (field f = tid % NF, orders m = tid / NF + i * NTHREADS / NF); fields fastest so
+    // that a warp reads full 64/128-byte groups of G.  NF is a power of two.
+    const bool simple = 2 * N < K;                     // no aliasing: every slot is written at most once
+    const int fsh = 31 - __clz(NF);
+    const int f = tid & (NF - 1), mstep = NTHREADS >> fsh;
+    double2* xf = smem2 + (size_t)f * fp.stride;
+    const bool flive = b0 + f < batch;
+    const int64_t gstep = (int64_t)R * 2 * t.Gs;       // G stride between consecutive orders
+    const double* gcol = G + ((int64_t)row * 2) * t.Gs + colidx(0, b0 + f, t.GS);
+    if (simple) {
+        // slots N < k < K-N receive nothing: zero them (and everything for a padded field)
+        for (int k = N + 1 + (tid >> fsh); k < K - N; k += mstep) xf[padi(perm[k])] = make_double2(0.0, 0.0);
+        if (!flive)
+            for (int k = tid >> fsh; k < K; k += mstep) xf[padi(k)] = make_double2(0.0, 0.0);
+    } else {
+        for (int i = tid; i < NF * fp.stride; i += NTHREADS) smem2[i] = make_double2(0.0, 0.0);
+        __syncthreads();
+    }
     const int nrounds = simple ? 1 : (N + K) / K;
     for (int rnd = 0; rnd < nrounds; ++rnd) {
         const int mlo = rnd * K, mhi = min(N, mlo + K - 1);
         for (int sub = 0; sub < (simple ? 1 : 2); ++sub) {
-            const int nitems = (mhi - mlo + 1) * NF;
-            constexpr int UN = 4;                       // independent (order, field) items in flight per thread
-            for (int base = tid; base < nitems; base += NTHREADS * UN) {
+            constexpr int UN = 4;                       // independent orders in flight per thread
+            for (int m0 = mlo + (tid >> fsh); m0 <= mhi; m0 += mstep * UN) {
                 double Ec[UN], Es[UN], Oc[UN], Os[UN];
                 double2 ph[UN];
                 int pk[UN], pkc[UN];
                 bool ok[UN];
 #pragma unroll
                 for (int u = 0; u < UN; ++u) {
-                    const int idx = base + u * NTHREADS;
-                    const int mm = idx / NF, f = idx - mm * NF;
-                    ok[u] = idx < nitems && b0 + f < batch;
+                    const int m = m0 + u * mstep;
+                    ok[u] = flive && m <= mhi;
                     if (ok[u]) {
-                        const double* g = G + (((int64_t)(mlo + mm) * R + row) * 2) * t.Gs + colidx(0, b0 + f, t.GS);
+                        const double* g = gcol + (int64_t)m * gstep;
                         Ec[u] = g[0]; Es[u] = g[t.GS]; Oc[u] = g[t.Gs]; Os[u] = g[t.Gs + t.GS];
-                        ph[u] = t.phase[mlo + mm];
-                        pk[u] = perm[mm]; pkc[u] = perm[(K - mm) % K];
+                        ph[u] = t.phase[m];
+                        const int mm = m - mlo;
+                        pk[u] = perm[mm]; pkc[u] = perm[mm ? K - mm : 0];
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < UN; ++u) {
                     if (!ok[u]) continue;
-                    const int idx = base + u * NTHREADS;
-                    const int mm = idx / NF, f = idx - mm * NF;
-                    const double2 Z = cmul(make_double2(Ec[u] + Oc[u], -(Es[u] + Os[u])), ph[u]);          // (A - iB) e^{i m lon0}, primary row
-                    const double2 Zp = mirror ? cmul(make_double2(Ec[u] - Oc[u], -(Es[u] - Os[u])), ph[u]) : make_double2(0.0, 0.0);
-                    const double2 Wa = make_double2(0.5 * (Z.x - Zp.y), 0.5 * (Z.y + Zp.x));              // (Z + i Z')/2        -> k =  m mod K
-                    const double2 Wb = make_double2(0.5 * (Z.x + Zp.y), 0.5 * (-Z.y + Zp.x));             // (conj Z + i conj Z')/2 -> k = -m mod K
-                    double2* x = smem2 + (size_t)f * fp.stride;
+                    // primary row: A = Ec+Oc, B = Es+Os; mirror row: A' = Ec-Oc, B' = Es-Os (zero without a mirror row)
+                    // Wa = (Z + iZ')/2 = [(A+B') + i(A'-B)] ph/2 -> k = m mod K ; Wb = (conj Z + i conj Z')/2 = [(A-B') + i(A'+B)] conj(ph)/2 -> k = -m mod K
+                    const double A = Ec[u] + Oc[u], B = Es[u] + Os[u];
+                    const double Ap = mirror ? Ec[u] - Oc[u] : 0.0, Bp_ = mirror ? Es[u] - Os[u] : 0.0;
+                    const double2 hp = make_double2(0.5 * ph[u].x, 0.5 * ph[u].y);
+                    const double2 Wa = cmul(make_double2(A + Bp_, Ap - B), hp);
+                    const double2 Wb = cmul(make_double2(A - Bp_, Ap + B), cconj(hp));
                     if (simple) {
-                        if (mm == 0) x[padi(pk[u])] = cadd(Wa, Wb);
-                        else { x[padi(pk[u])] = Wa; x[padi(pkc[u])] = Wb; }
+                        if (m0 + u * mstep == 0) xf[padi(pk[u])] = cadd(Wa, Wb);
+                        else { xf[padi(pk[u])] = Wa; xf[padi(pkc[u])] = Wb; }
                     } else if (sub == 0) {
-                        double2* p = &x[padi(pk[u])]; *p = cadd(*p, Wa);
+                        double2* p = &xf[padi(pk[u])]; *p = cadd(*p, Wa);
                     } else {
-                        double2* p = &x[padi(pkc[u])]; *p = cadd(*p, Wb);
+                        double2* p = &xf[padi(pkc[u])]; *p = cadd(*p, Wb);
                     }
                 }
             }
@@ -283,23 +298,33 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_ana_fft(DevTables t, Params 
         if (s > 0) group_sync(1 + tr, fp.TPT);
     }
     __syncthreads();
-    for (int idx = tid; idx < (N + 1) * NF; idx += NTHREADS) {
-        const int m = idx / NF, f = idx - m * NF;
+    {
+        // thread <-> (field f = tid % NF, orders m = tid / NF + i * NTHREADS / NF)
+        const int fsh = 31 - __clz(NF);
+        const int f = tid & (NF - 1), mstep = NTHREADS >> fsh;
         const int b = b0 + f;
-        if (b >= Bp) continue;
-        const double2* xx = smem2 + (size_t)f * fp.stride;
-        const int k = m % K, kc = (K - k) % K;
-        const double2 Wk = xx[padi(perm[k])], Wc = cconj(xx[padi(perm[kc])]);
-        const double2 F = make_double2(0.5 * (Wk.x + Wc.x), 0.5 * (Wk.y + Wc.y));      // spectrum of the primary row
-        const double2 D = csub(Wk, Wc);
-        const double2 Fp = make_double2(0.5 * D.y, -0.5 * D.x);                        // (Wk - conj W_{K-k}) / (2i): mirror row
-        const double2 phc = cconj(t.phase[m]);
-        const double2 Z = cmul(F, phc), Zp = cmul(Fp, phc);                            // a_m - i b_m
-        const double a = w1 * Z.x, bb = -w1 * Z.y, ap = w2 * Zp.x, bp = -w2 * Zp.y;
-        double* g = G + (((int64_t)m * R + row) * 2) * t.Gs + colidx(0, b, t.GS);
-        const bool live = b < batch;
-        g[0] = live ? a + ap : 0.0; g[t.GS] = live ? bb + bp : 0.0;
-        g[t.Gs] = live ? a - ap : 0.0; g[t.Gs + t.GS] = live ? bb - bp : 0.0;
+        if (b < Bp) {
+            const double2* xx = smem2 + (size_t)f * fp.stride;
+            const bool live = b < batch;
+            const int64_t gstep = (int64_t)R * 2 * t.Gs;
+            double* gcol = G + ((int64_t)row * 2) * t.Gs + colidx(0, b, t.GS);
+            int k = (tid >> fsh) % K;
+            const int kstep = mstep % K;
+            for (int m = tid >> fsh; m <= N; m += mstep) {
+                const int kc = k ? K - k : 0;
+                const double2 Wk = xx[padi(perm[k])], Wc = cconj(xx[padi(perm[kc])]);
+                k += kstep; if (k >= K) k -= K;
+                const double2 F = make_double2(0.5 * (Wk.x + Wc.x), 0.5 * (Wk.y + Wc.y));      // spectrum of the primary row
+                const double2 D = csub(Wk, Wc);
+                const double2 Fp = make_double2(0.5 * D.y, -0.5 * D.x);                        // (Wk - conj W_{K-k}) / (2i): mirror row
+                const double2 phc = cconj(t.phase[m]);
+                const double2 Z = cmul(F, phc), Zp = cmul(Fp, phc);                            // a_m - i b_m
+                const double a = w1 * Z.x, bb = -w1 * Z.y, ap = w2 * Zp.x, bp = -w2 * Zp.y;
+                double* g = gcol + (int64_t)m * gstep;
+                g[0] = live ? a + ap : 0.0; g[t.GS] = live ? bb + bp : 0.0;
+                g[t.Gs] = live ? a - ap : 0.0; g[t.Gs + t.GS] = live ? bb - bp : 0.0;
+            }
+        }
     }
 }
 
