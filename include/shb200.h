@@ -91,6 +91,14 @@ int shb200_plan_get_info(const shb200_plan* plan, shb200_plan_info* info);
  * the launching stream; the call synchronises that stream's last event.  Used by bench.py for the roofline. */
 int shb200_plan_stage_times(shb200_plan* plan, double* ms, int32_t n);
 
+/* Fused isotropic kernel: per-degree scale applied while the coefficients are packed (which=0,
+ * synthesis input) or unpacked (which=1, analysis output).  This is what shxarray's isotropic operators do on the host
+ * before/after a transform -- Gaussian filter, gravity functionals stokes<->tws/geoid/uplift: IsoKernelBase.__call__
+ * src/shxarray/kernels/isokernelbase.py:75-92 (dain * expanddiag(nm)).  scale: host array of nmax+1 doubles indexed by degree,
+ * copied by the call; NULL switches the scale off.  The product c*scale[n] is one IEEE multiplication, i.e. bit-identical to
+ * scaling on the host first. */
+int shb200_plan_set_degree_scale(shb200_plan* plan, int32_t which, const double* scale, int32_t n);
+
 /* Synthesis  f(b, point) = sum_k C(b,k) * Ybar_{n_k m_k}(point)      [synthesis.pyx:175-189]
  *   coef element (b,k)          at coef[b*cs_b + k*cs_nm]             (device pointer, element strides)
  *   grid element (b,ilat,ilon)  at grid[b*gs_b + ilat*gs_lat + ilon*gs_lon]; point mode: (b,i) at grid[b*gs_b + i*gs_lat]

@@ -21,7 +21,7 @@ FLAG_NO_SYMMETRY, FLAG_DENSE_LON, FLAG_NO_DMMA, FLAG_TIMING, FLAG_NO_PTABLE = 1,
 EXPORTS = [
     "shb200_version", "shb200_last_error", "shb200_plan_create", "shb200_plan_destroy", "shb200_plan_get_info",
     "shb200_synthesis", "shb200_analysis", "shb200_synthesis_host", "shb200_analysis_host", "shb200_multiply",
-    "shb200_gauss_nodes", "shb200_debug_legendre", "shb200_plan_stage_times",
+    "shb200_gauss_nodes", "shb200_debug_legendre", "shb200_plan_stage_times", "shb200_plan_set_degree_scale",
 ]
 
 
@@ -74,6 +74,7 @@ def lib():
     L.shb200_analysis_host.argtypes = [vp, i32, vp, i64, i64, i64, vp, i64, i64]
     L.shb200_multiply.argtypes = [vp, vp, vp, i32, vp, i64, i64, vp, i64, i64, vp, i64, i64, vp]
     L.shb200_plan_stage_times.argtypes = [vp, vp, i32]
+    L.shb200_plan_set_degree_scale.argtypes = [vp, i32, vp, i32]
     L.shb200_gauss_nodes.argtypes = [i32, vp, vp]
     L.shb200_debug_legendre.argtypes = [i32, i32, dbl, vp]
     for name in EXPORTS:
@@ -181,6 +182,14 @@ class Plan:
     def multiply_dev(self, syn_b, ana, batch, a_ptr, as_b, as_nm, b_ptr, bs_b, bs_nm, out_ptr, os_b, os_nm, stream=0):
         """self = synthesis plan of operand a; syn_b = synthesis plan of operand b; ana = analysis plan (same grid)."""
         check(lib().shb200_multiply(self._h, syn_b._h, ana._h, batch, a_ptr, as_b, as_nm, b_ptr, bs_b, bs_nm, out_ptr, os_b, os_nm, stream))
+
+    def set_degree_scale(self, which, scale):
+        """which: 0 = synthesis input, 1 = analysis output; scale: nmax+1 per-degree factors or None to switch off."""
+        if scale is None:
+            check(lib().shb200_plan_set_degree_scale(self._h, int(which), None, 0))
+        else:
+            s = np.ascontiguousarray(scale, dtype=np.float64)
+            check(lib().shb200_plan_set_degree_scale(self._h, int(which), s.ctypes.data, len(s)))
 
     def stage_times(self):
         """dict of per-stage device ms of the last synthesis/analysis (plan needs FLAG_TIMING)."""

@@ -94,6 +94,9 @@ struct Plan {
     const int64_t* dup_slot = nullptr;  // device [ndup] slot*2+cs
     const int64_t* dup_src = nullptr;   // device [ndup]
     const int64_t* fwd_slot = nullptr;  // device [nsh] list index -> slot*2+cs (-1 for repeated entries)
+    const int32_t* deg_of_k = nullptr;  // device [nsh] degree of each list entry
+    double* dscale[2] = {nullptr, nullptr};   // device [nmax+1] per-degree scales (synthesis input / analysis output)
+    bool dscale_on[2] = {false, false};
     // staging for the *_host entry points
     double* stage_coef = nullptr; int64_t stage_coef_elems = 0;
     double* stage_grid = nullptr; int64_t stage_grid_elems = 0;

@@ -14,6 +14,8 @@
 // digit-reversed slot, natural-order output -> coalesced row stores), decimation in frequency for analysis (natural
 // input, spectrum picked up from the digit-reversed slots).  NF consecutive fields of one latitude pair per CTA so that
 // every G access is a full 64 B segment.
+#include <cstdlib>
+
 #include "internal.h"
 
 namespace shb {
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_syn_fft(DevTables t, Params 
                                                              double* __restrict__ grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon) {
     extern __shared__ double2 smem2[];
     const int K = fp.K, N = t.nmax, R = t.nrows, NC = t.NC, Bp = t.Bp, NF = fp.NF;
-    const int row = blockIdx.x, b0 = blockIdx.y * NF;
+    const int row = blockIdx.y, b0 = blockIdx.x * NF;
     const int tid = threadIdx.x, NTHREADS = blockDim.x;
     const int i1 = t.row_i1[row], i2 = t.row_i2[row];
     const bool mirror = i2 >= 0;
@@ -265,7 +267,7 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_ana_fft(DevTables t, Params 
                                                              int64_t gs_b, int64_t gs_lat, int64_t gs_lon, double* __restrict__ G) {
     extern __shared__ double2 smem2[];
     const int K = fp.K, N = t.nmax, R = t.nrows, NC = t.NC, Bp = t.Bp, NF = fp.NF;
-    const int row = blockIdx.x, b0 = blockIdx.y * NF;
+    const int row = blockIdx.y, b0 = blockIdx.x * NF;
     const int tid = threadIdx.x, NTHREADS = blockDim.x;
     const int i1 = t.row_i1[row], i2 = t.row_i2[row];
     const bool mirror = i2 >= 0;
@@ -351,6 +353,10 @@ static bool fft_params(int K, int Bp, fft::Params& fp) {
     for (int c = 1; c <= 8 && c <= Bp; c *= 2)
         if (c * per <= 220 * 1024) nf = c;
     if (nf == 0) return false;
+    {
+        const char* e = getenv("SHB200_FFT_NF");
+        if (e && atoi(e) > 0 && atoi(e) < nf) nf = atoi(e);
+    }
     fp.NF = nf;
     fp.TPT = nf >= 4 ? 64 : (nf == 2 ? 128 : 256);
     fp.nthreads = fp.NF * fp.TPT;
@@ -380,7 +386,7 @@ int launch_lon_syn_fft(const Plan& p, int batch, double* grid, int64_t gs_b, int
     size_t smem = (size_t)fp.NF * fp.stride * sizeof(double2);
     static bool attr = false;
     if (!attr) { SHB_CUDA(cudaFuncSetAttribute(fft::k_lon_syn_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
-    dim3 g(p.nrows, (batch + fp.NF - 1) / fp.NF);
+    dim3 g((batch + fp.NF - 1) / fp.NF, p.nrows);
     fft::k_lon_syn_fft<<<g, fp.nthreads, smem, st>>>(p.t, fp, p.fft_perm, batch, p.G, grid, gs_b, gs_lat, gs_lon);
     return 0;
 }
@@ -391,7 +397,7 @@ int launch_lon_ana_fft(const Plan& p, int batch, const double* grid, int64_t gs_
     size_t smem = (size_t)fp.NF * fp.stride * sizeof(double2);
     static bool attr = false;
     if (!attr) { SHB_CUDA(cudaFuncSetAttribute(fft::k_lon_ana_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
-    dim3 g(p.nrows, (p.Bp + fp.NF - 1) / fp.NF);
+    dim3 g((p.Bp + fp.NF - 1) / fp.NF, p.nrows);
     fft::k_lon_ana_fft<<<g, fp.nthreads, smem, st>>>(p.t, fp, p.fft_perm, batch, grid, gs_b, gs_lat, gs_lon, p.G);
     return 0;
 }

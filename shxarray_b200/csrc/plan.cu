@@ -87,8 +87,10 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
     // ---- nm list -> slot map -----------------------------------------------------------------
     std::vector<int64_t> slot_src((size_t)T * 2, -1);
     std::vector<int64_t> dup_slot, dup_src, fwd;
+    std::vector<int32_t> degk;
     if (d.nsh > 0) {
         fwd.assign((size_t)d.nsh, -1);
+        degk.assign(d.n, d.n + d.nsh);
         if (!d.n || !d.m) { set_error("plan_create: nsh > 0 but n/m arrays are null"); return SHB200_EINVAL; }
         p.nsh = d.nsh;
         p.full_triangle = (d.nsh == (int64_t)(N + 1) * (N + 1));
@@ -104,6 +106,9 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
         p.nsh = (int64_t)(N + 1) * (N + 1);
         p.full_triangle = true;
         fwd.assign((size_t)p.nsh, -1);
+        degk.resize((size_t)p.nsh);
+        for (int n = 0; n <= N; ++n)
+            for (int m = -n; m <= n; ++m) degk[(int64_t)n * n + n + m] = n;
         for (int n = 0; n <= N; ++n)
             for (int m = -n; m <= n; ++m) {
                 int am = m < 0 ? -m : m;
@@ -243,6 +248,12 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
     if ((rc = upload(p, dup_slot, &p.dup_slot))) return rc;
     if ((rc = upload(p, dup_src, &p.dup_src))) return rc;
     if ((rc = upload(p, fwd, &p.fwd_slot))) return rc;
+    if ((rc = upload(p, degk, &p.deg_of_k))) return rc;
+    for (int w = 0; w < 2; ++w) {
+        void* q;
+        if ((rc = dev_alloc(p, sizeof(double) * (N + 1), &q))) return rc;
+        p.dscale[w] = (double*)q;
+    }
     t.nmax = N; t.nrows = R; t.nlat = d.nlat; t.nlon = d.nlon; t.Bp = p.Bp; t.NC = p.NC; t.GS = p.Bp >= 8 ? 8 : 4;
     t.Cs = p.NC + 2; t.Gs = p.NC; t.pt_base = nullptr; t.RT32 = 0;
 
@@ -376,6 +387,17 @@ int shb200_analysis(shb200_plan* plan, int32_t batch, const double* grid, int64_
     launch_unpack(p, batch, coef, cs_b, cs_nm, st);
     if (tm) { cudaEventRecord(p.ev[7], st); p.timed_ana = true; }
     SHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int shb200_plan_set_degree_scale(shb200_plan* plan, int32_t which, const double* scale, int32_t n) {
+    if (!plan || which < 0 || which > 1) { set_error("set_degree_scale: bad plan or selector"); return SHB200_EINVAL; }
+    Plan& p = plan->p;
+    if (!scale) { p.dscale_on[which] = false; return 0; }
+    if (n != p.nmax + 1) { set_error("set_degree_scale: need nmax+1 values"); return SHB200_EINVAL; }
+    SHB_CUDA(cudaSetDevice(p.device));
+    SHB_CUDA(cudaMemcpy(p.dscale[which], scale, sizeof(double) * n, cudaMemcpyHostToDevice));
+    p.dscale_on[which] = true;
     return 0;
 }
 

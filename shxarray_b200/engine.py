@@ -195,7 +195,7 @@ class SHEngine:
 
     # ------------------------------------------------------------------------------------------
     def synthesis(self, coef, n=None, m=None, lon=None, lat=None, nmax=None, points=False, nm_axis=-1,
-                  layout="batch_first", out=None, flags=None):
+                  layout="batch_first", out=None, flags=None, degree_scale=None):
         """Spherical-harmonic synthesis of a batch of coefficient vectors.
 
         coef : [B, nsh] (``nm_axis=-1``) or [nsh, B] (``nm_axis=0``) or [nsh]; numpy (host) or torch CUDA tensor.
@@ -203,6 +203,8 @@ class SHEngine:
                in nm order for ``nmax``.
         lon, lat : degrees.  ``points=True``: paired points (synthesis.pyx:186-189) else tensor grid.
         layout : 'batch_first' -> [B, nlat, nlon] ; 'shlib' -> [nlat, nlon, B] (synthesis.pyx:68-71).
+        degree_scale : optional nmax+1 per-degree factors fused into the transform (isotropic kernels: Gaussian filter,
+               gravity functionals; isokernelbase.py:75-92) -- identical to scaling the coefficients first.
         """
         lon = np.ascontiguousarray(lon, dtype=np.float64)
         lat = np.ascontiguousarray(lat, dtype=np.float64)
@@ -241,6 +243,7 @@ class SHEngine:
         if points and len(lon) != len(lat):
             raise ValueError("point synthesis needs equally sized lon and lat")
         plan = self.get_plan(nmax, lat, lon, B, n=n, m=m, mode=mode, flags=flags)
+        plan.set_degree_scale(0, degree_scale)
         L, K = len(lat), len(lon)
         if points:
             shape = (B, L) if layout == "batch_first" else (L, B)
@@ -281,7 +284,7 @@ class SHEngine:
 
     # ------------------------------------------------------------------------------------------
     def analysis(self, grid, nmax, lon, lat, quadrature="shlib", lat_weights=None, weight=None, layout="batch_first",
-                 out=None, flags=None):
+                 out=None, flags=None, degree_scale=None):
         """Spherical-harmonic analysis of a batch of lon/lat grids (analysis.pyx:31-139).
 
         grid : [B, nlat, nlon] ('batch_first') or [nlat, nlon, B] ('shlib'); any strides; numpy or torch CUDA.
@@ -322,6 +325,7 @@ class SHEngine:
         else:
             raise ValueError("quadrature must be 'shlib', 'gauss' or 'weights'")
         plan = self.get_plan(nmax, lat, lon, B, quadrature=q, weight=wgt, lat_weights=lw, flags=flags)
+        plan.set_degree_scale(1, degree_scale)
         nsh = (nmax + 1) ** 2
         if tor:
             import torch

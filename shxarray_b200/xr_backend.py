@@ -91,7 +91,11 @@ class B200Backend(SHComputeBackendBase):
         dast, auxdim = _stack_aux(dain, ["nm"])
         dast = dast.transpose(auxdim, "nm")
         coef = np.asarray(dast.data, dtype=np.float64)           # [B, nsh], any strides
-        out = self._engine.synthesis(coef, n, m, lon, lat, points=points)
+        # degree_scale=<nmax+1 factors or an IsoKernelBase> fuses an isotropic kernel into the transform
+        ds = kwargs.get("degree_scale", None)
+        if ds is not None and hasattr(ds, "_dsiso"):
+            ds = np.asarray(ds._dsiso.sel(n=np.arange(int(n.max()) + 1)).data, dtype=np.float64)
+        out = self._engine.synthesis(coef, n, m, lon, lat, points=points, degree_scale=ds)
         if points:
             pdim = latinfo.var.dims[0]
             coords = {auxdim: dast.coords[auxdim], "lat": (pdim, lat), "lon": (pdim, lon)}
@@ -133,7 +137,10 @@ class B200Backend(SHComputeBackendBase):
         grid = np.asarray(dast.data, dtype=np.float64)
         lon = np.asarray(loninfo.var.data, dtype=np.float64)
         lat = np.asarray(latinfo.var.data, dtype=np.float64)
-        out = self._engine.analysis(grid, int(nmax), lon, lat, quadrature=quadrature)
+        ds = kwargs.get("degree_scale", None)
+        if ds is not None and hasattr(ds, "_dsiso"):
+            ds = np.asarray(ds._dsiso.sel(n=np.arange(int(nmax) + 1)).data, dtype=np.float64)
+        out = self._engine.analysis(grid, int(nmax), lon, lat, quadrature=quadrature, degree_scale=ds)
         coords = {auxdim: dast.coords[auxdim], SHindexBase.name: SHindexBase.nm_mi(int(nmax), 0)}
         daout = xr.DataArray(out, coords=coords, dims=[auxdim, SHindexBase.name])
         daout = _unstack_aux(daout, auxdim)

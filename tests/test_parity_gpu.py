@@ -348,3 +348,26 @@ def test_descending_and_shuffled_latitudes(engine):
     aref = O.analysis(f, nmax, lon, lat, kind="port")
     aout = engine.analysis(f, nmax, lon, lat, quadrature="shlib")
     assert per_field_err(aout, aref) <= TOL
+
+
+def test_fused_degree_scale_is_bit_identical_to_host_scaling(engine):
+    """isotropic kernels (Gaussian filter, gravity functionals) are a per-degree scale,
+    IsoKernelBase.__call__ (isokernelbase.py:75-92).  Fused into pack/unpack it must equal scaling on the host."""
+    nmax, B = 96, 9
+    n, m = sb.nm_index(nmax)
+    c = S.random_coefficients(nmax, B, kaula=True, seed=12)
+    g = sb.lonlat_grid(nmax, gtype="regular")
+    # a Gaussian-filter-like and an EWH-like scale (synthetic load Love numbers, SURVEY.md §8d)
+    deg = np.arange(nmax + 1, dtype=np.float64)
+    scale = np.exp(-deg * (deg + 1) * 1e-3) * (2 * deg + 1) / (1 - 0.3 / (deg + 1))
+    fused = engine.synthesis(c, n, m, g["lon"], g["lat"], degree_scale=scale)
+    host = engine.synthesis(c * scale[n][None, :], n, m, g["lon"], g["lat"])
+    assert np.array_equal(fused, host)
+    plain = engine.synthesis(c, n, m, g["lon"], g["lat"])           # the scale is switched off again
+    assert not np.array_equal(plain, fused)
+    a_f = engine.analysis(host, nmax, g["lon"], g["lat"], degree_scale=1.0 / scale)
+    a_h = engine.analysis(host, nmax, g["lon"], g["lat"]) * (1.0 / scale)[n][None, :]
+    assert np.array_equal(a_f, a_h)
+    # nm-first memory layout goes through the other pack kernel
+    fused_t = engine.synthesis(np.ascontiguousarray(c.T), n, m, g["lon"], g["lat"], nm_axis=0, degree_scale=scale)
+    assert np.array_equal(fused_t, fused)
