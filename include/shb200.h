@@ -99,6 +99,12 @@ int shb200_plan_stage_times(shb200_plan* plan, double* ms, int32_t n);
  * scaling on the host first. */
 int shb200_plan_set_degree_scale(shb200_plan* plan, int32_t which, const double* scale, int32_t n);
 
+/* Multi-GPU m-order sharding of ANALYSIS: the plan integrates only the orders m = rank, rank+world,
+ * rank+2*world, ... (interleaved: work per order is proportional to nmax-m+1) and writes exact zeros for every other
+ * coefficient, so that summing (or gathering) the outputs of the `world` ranks gives the full result bit-identically to the
+ * unsharded transform.  rank=0, world=1 restores the default.  Synthesis is unaffected (it shards by latitude or batch). */
+int shb200_plan_set_order_shard(shb200_plan* plan, int32_t rank, int32_t world);
+
 /* Synthesis  f(b, point) = sum_k C(b,k) * Ybar_{n_k m_k}(point)      [synthesis.pyx:175-189]
  *   coef element (b,k)          at coef[b*cs_b + k*cs_nm]             (device pointer, element strides)
  *   grid element (b,ilat,ilon)  at grid[b*gs_b + ilat*gs_lat + ilon*gs_lon]; point mode: (b,i) at grid[b*gs_b + i*gs_lat]

@@ -21,7 +21,7 @@ FLAG_NO_SYMMETRY, FLAG_DENSE_LON, FLAG_NO_DMMA, FLAG_TIMING, FLAG_NO_PTABLE = 1,
 EXPORTS = [
     "shb200_version", "shb200_last_error", "shb200_plan_create", "shb200_plan_destroy", "shb200_plan_get_info",
     "shb200_synthesis", "shb200_analysis", "shb200_synthesis_host", "shb200_analysis_host", "shb200_multiply",
-    "shb200_gauss_nodes", "shb200_debug_legendre", "shb200_plan_stage_times", "shb200_plan_set_degree_scale",
+    "shb200_gauss_nodes", "shb200_debug_legendre", "shb200_plan_stage_times", "shb200_plan_set_degree_scale", "shb200_plan_set_order_shard",
 ]
 
 
@@ -75,6 +75,7 @@ def lib():
     L.shb200_multiply.argtypes = [vp, vp, vp, i32, vp, i64, i64, vp, i64, i64, vp, i64, i64, vp]
     L.shb200_plan_stage_times.argtypes = [vp, vp, i32]
     L.shb200_plan_set_degree_scale.argtypes = [vp, i32, vp, i32]
+    L.shb200_plan_set_order_shard.argtypes = [vp, i32, i32]
     L.shb200_gauss_nodes.argtypes = [i32, vp, vp]
     L.shb200_debug_legendre.argtypes = [i32, i32, dbl, vp]
     for name in EXPORTS:
@@ -190,6 +191,10 @@ class Plan:
         else:
             s = np.ascontiguousarray(scale, dtype=np.float64)
             check(lib().shb200_plan_set_degree_scale(self._h, int(which), s.ctypes.data, len(s)))
+
+    def set_order_shard(self, rank=0, world=1):
+        """analysis integrates only orders m = rank (mod world); other coefficients come out as exact zeros."""
+        check(lib().shb200_plan_set_order_shard(self._h, int(rank), int(world)))
 
     def stage_times(self):
         """dict of per-stage device ms of the last synthesis/analysis (plan needs FLAG_TIMING)."""

@@ -48,6 +48,7 @@ struct DevTables {
                           // 16 B mod 64 B, so a CONTIGUOUS block of rows lands in shared memory as a bank-conflict-free padded
                           // tile with a single cp.async.bulk (legendre_tab.cu).  G keeps 128-byte aligned rows: the longitude
                           // stage touches it in 128-byte groups and lost 20 % when its rows were padded the same way (r01).
+    int m0, mstride;         // analysis order shard: this plan integrates orders m = m0 + i*mstride only (multi-GPU m-sharding)
     const int64_t* pt_base;  // [nmax+2] first 16-degree block of each order in the tiled P table
     int RT32;                // row tiles (of 32) in the P table = Rpad/32
 };
@@ -105,6 +106,9 @@ struct Plan {
     cudaEvent_t ev[8] = {};     // SHB200_FLAG_TIMING: syn 0..3, ana 4..7
     bool timed_syn = false, timed_ana = false;
 };
+
+// number of orders m = m0, m0+mstride, ... <= nmax integrated by this plan's analysis
+inline int ana_order_count(const Plan& p) { return p.t.m0 > p.nmax ? 0 : (p.nmax - p.t.m0) / p.t.mstride + 1; }
 
 }  // namespace shb
 

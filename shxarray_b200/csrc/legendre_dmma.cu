@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(ana::NTHREADS, 1) k_leg_ana_dmma(DevTables t, 
     uint64_t* gfull = pempty + PSTAGES;
     uint64_t* gempty = gfull + 2;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m = blockIdx.x, col0 = blockIdx.y * NCOLS;
+    const int m = t.m0 + t.mstride * blockIdx.x, col0 = blockIdx.y * NCOLS;
     const int N = t.nmax, R = t.nrows, NC = t.NC;
     const int ncols = min(NCOLS, NC - col0);
     const int nsb = (N - m + SB) / SB;                 // super-blocks
@@ -334,7 +334,7 @@ bool launch_legendre_ana_dmma(const Plan& p, cudaStream_t st) {
         if (cudaFuncSetAttribute(k_leg_ana_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ana::smem_bytes(ana::MAXROWS)) != cudaSuccess) return false;
         attr = true;
     }
-    dim3 grid(p.nmax + 1, (p.NC + ana::NCOLS - 1) / ana::NCOLS);
+    dim3 grid(ana_order_count(p), (p.NC + ana::NCOLS - 1) / ana::NCOLS);
     k_leg_ana_dmma<<<grid, ana::NTHREADS, smem, st>>>(p.t, p.G, p.Cm, rows_padded);
     return true;
 }

@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(ta::NTHREADS, 1) k_leg_ana_tab(DevTables t, co
     uint64_t* gfull = pempty + PSTAGES;
     uint64_t* gempty = gfull + 2;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m = blockIdx.x, col0 = blockIdx.y * NCOLS;
+    const int m = t.m0 + t.mstride * blockIdx.x, col0 = blockIdx.y * NCOLS;
     const int N = t.nmax, R = t.nrows, NC = t.NC;
     const int ncols = min(NCOLS, NC - col0);
     const int nsb = (N - m + SB) / SB;
@@ -309,7 +309,7 @@ bool launch_legendre_ana_tab(const Plan& p, cudaStream_t st) {
         if (cudaFuncSetAttribute(k_leg_ana_tab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ta::SMEM) != cudaSuccess) return false;
         attr = true;
     }
-    dim3 grid(p.nmax + 1, (p.NC + ta::NCOLS - 1) / ta::NCOLS);
+    dim3 grid(ana_order_count(p), (p.NC + ta::NCOLS - 1) / ta::NCOLS);
     k_leg_ana_tab<<<grid, ta::NTHREADS, ta::SMEM, st>>>(p.t, p.Ptab, p.G, p.Cm);
     return true;
 }

@@ -314,8 +314,10 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_ana_fft(DevTables t, Params 
             const int kstep = mstep % K;
             for (int m = tid >> fsh; m <= N; m += mstep) {
                 const int kc = k ? K - k : 0;
-                const double2 Wk = xx[padi(perm[k])], Wc = cconj(xx[padi(perm[kc])]);
+                const int kcur = k;
                 k += kstep; if (k >= K) k -= K;
+                if (m < t.m0 || (m - t.m0) % t.mstride) continue;          // order integrated on another rank (m-sharding)
+                const double2 Wk = xx[padi(perm[kcur])], Wc = cconj(xx[padi(perm[kc])]);
                 const double2 F = make_double2(0.5 * (Wk.x + Wc.x), 0.5 * (Wk.y + Wc.y));      // spectrum of the primary row
                 const double2 D = csub(Wk, Wc);
                 const double2 Fp = make_double2(0.5 * D.y, -0.5 * D.x);                        // (Wk - conj W_{K-k}) / (2i): mirror row

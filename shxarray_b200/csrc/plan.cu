@@ -255,7 +255,7 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
         p.dscale[w] = (double*)q;
     }
     t.nmax = N; t.nrows = R; t.nlat = d.nlat; t.nlon = d.nlon; t.Bp = p.Bp; t.NC = p.NC; t.GS = p.Bp >= 8 ? 8 : 4;
-    t.Cs = p.NC + 2; t.Gs = p.NC; t.pt_base = nullptr; t.RT32 = 0;
+    t.Cs = p.NC + 2; t.Gs = p.NC; t.pt_base = nullptr; t.RT32 = 0; t.m0 = 0; t.mstride = 1;
 
     void* ptr;
     // 16 / 64 slack rows: the tensor-core kernels fetch whole 16-degree / 32-row blocks, also past the last order
@@ -398,6 +398,13 @@ int shb200_plan_set_degree_scale(shb200_plan* plan, int32_t which, const double*
     SHB_CUDA(cudaSetDevice(p.device));
     SHB_CUDA(cudaMemcpy(p.dscale[which], scale, sizeof(double) * n, cudaMemcpyHostToDevice));
     p.dscale_on[which] = true;
+    return 0;
+}
+
+int shb200_plan_set_order_shard(shb200_plan* plan, int32_t rank, int32_t world) {
+    if (!plan || world < 1 || rank < 0 || rank >= world) { set_error("set_order_shard: need 0 <= rank < world"); return SHB200_EINVAL; }
+    plan->p.t.m0 = rank;
+    plan->p.t.mstride = world;
     return 0;
 }
 

@@ -11,6 +11,11 @@ synthesis.pyx:179, analysis.pyx:128).  The path shards three ways (SURVEY.md §8
   reduction (optional all_gather of the grid rows); analysis produces per-rank partial quadrature sums that
   one all_reduce(SUM) of the coefficient vector combines -- the only real exchange step of the path.
 
+* m-order sharding of a single analysis (what BASELINE's config 4 names) -- every rank holds the grid, runs the cheap
+  longitude stage for all rows and integrates only the orders m = rank (mod world) (interleaved because the work per
+  order is proportional to nmax-m+1); all other coefficients come out as exact zeros, so one all_reduce(SUM) -- a gather
+  in effect, 37 MB at nmax 2160 -- assembles the full vector bit-identically to the unsharded transform.
+
 The engine is injectable so the planner logic is testable on CPU (world_size 2, gloo) with the oracle.
 """
 import numpy as np
@@ -122,6 +127,19 @@ class ShardedSH:
         else:
             sub = np.ascontiguousarray(np.asarray(grid)[:, rows, :])
         part = self.engine.analysis(sub, nmax, lon, lat[rows], quadrature="weights", lat_weights=lw[rows], weight=weight, **kw)
+        if self.d.world == 1:
+            return part
+        is_t = hasattr(part, "is_cuda")
+        pt = part if is_t else torch.from_numpy(np.ascontiguousarray(part))
+        self.d.dist.all_reduce(pt, op=self.d.dist.ReduceOp.SUM, group=self.d.group)
+        return pt if is_t else pt.numpy()
+
+
+    def analysis_msharded(self, grid, nmax, lon, lat, **kw):
+        """grid [B, nlat, nlon] replicated on every rank; rank r integrates the orders m = r (mod world)
+        (shb200_plan_set_order_shard) and one all_reduce(SUM) over NVLink gathers the disjoint shards."""
+        import torch
+        part = self.engine.analysis(grid, nmax, lon, lat, order_shard=(self.d.rank, self.d.world), **kw)
         if self.d.world == 1:
             return part
         is_t = hasattr(part, "is_cuda")

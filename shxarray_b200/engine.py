@@ -284,7 +284,7 @@ class SHEngine:
 
     # ------------------------------------------------------------------------------------------
     def analysis(self, grid, nmax, lon, lat, quadrature="shlib", lat_weights=None, weight=None, layout="batch_first",
-                 out=None, flags=None, degree_scale=None):
+                 out=None, flags=None, degree_scale=None, order_shard=None):
         """Spherical-harmonic analysis of a batch of lon/lat grids (analysis.pyx:31-139).
 
         grid : [B, nlat, nlon] ('batch_first') or [nlat, nlon, B] ('shlib'); any strides; numpy or torch CUDA.
@@ -326,6 +326,7 @@ class SHEngine:
             raise ValueError("quadrature must be 'shlib', 'gauss' or 'weights'")
         plan = self.get_plan(nmax, lat, lon, B, quadrature=q, weight=wgt, lat_weights=lw, flags=flags)
         plan.set_degree_scale(1, degree_scale)
+        plan.set_order_shard(*(order_shard if order_shard is not None else (0, 1)))   # (rank, world): m-sharded analysis
         nsh = (nmax + 1) ** 2
         if tor:
             import torch

@@ -47,12 +47,20 @@ class OracleEngine:
         out = O.synthesis(np.asarray(coef), n, m, lon, lat, kind="port", nthreads=2)
         return np.ascontiguousarray(np.moveaxis(out, 2, 0))
 
-    def analysis(self, grid, nmax, lon, lat, quadrature="weights", lat_weights=None, weight=1.0, **kw):
+    def analysis(self, grid, nmax, lon, lat, quadrature="weights", lat_weights=None, weight=None, order_shard=None, **kw):
         from oracle import oracle as O
-        # the oracle applies weight*cos(lat); fold the requested per-latitude weight into the data instead
         lat = np.asarray(lat)
-        scale = np.asarray(lat_weights) / np.cos(lat * (np.pi / 180))
-        return O.analysis(np.asarray(grid) * scale[None, :, None], nmax, lon, lat, kind="port", weight=weight, nthreads=2)
+        if quadrature == "shlib":
+            out = O.analysis(np.asarray(grid), nmax, lon, lat, kind="port", nthreads=2)
+        else:
+            # the oracle applies weight*cos(lat); fold the requested per-latitude weight into the data instead
+            scale = np.asarray(lat_weights) / np.cos(lat * (np.pi / 180))
+            out = O.analysis(np.asarray(grid) * scale[None, :, None], nmax, lon, lat, kind="port", weight=weight, nthreads=2)
+        if order_shard is not None:          # emulate shb200_plan_set_order_shard: other ranks' orders are exact zeros
+            rank, world = order_shard
+            _, m = O.nm_index(nmax)
+            out = out * ((np.abs(m) % world) == rank)[None, :]
+        return out
 
 
 def _worker(rank, world, port, q):
@@ -82,6 +90,9 @@ def _worker(rank, world, port, q):
         part = sh.analysis_latsharded(ref, nmax, lon, lat, lat_weights=lw, weight=w)
         aref = O.analysis(ref, nmax, lon, lat, kind="port", nthreads=2)
         ok_ana = np.abs(part - aref).max() <= 1e-12 * np.abs(aref).max()
+        # m-order-sharded analysis + all_reduce (disjoint shards: the sum is a gather, exact)
+        msh = sh.analysis_msharded(ref, nmax, lon, lat, quadrature="shlib")
+        ok_ana = ok_ana and np.array_equal(msh, aref)
         q.put((rank, lo, hi, bool(ok_batch), bool(ok_syn), bool(ok_ana)))
     finally:
         dist.destroy_process_group()

@@ -371,3 +371,24 @@ def test_fused_degree_scale_is_bit_identical_to_host_scaling(engine):
     # nm-first memory layout goes through the other pack kernel
     fused_t = engine.synthesis(np.ascontiguousarray(c.T), n, m, g["lon"], g["lat"], nm_axis=0, degree_scale=scale)
     assert np.array_equal(fused_t, fused)
+
+
+@pytest.mark.parametrize("nmax,B,flags", [(64, 3, 0), (200, 40, 0), (200, 40, capi.FLAG_NO_PTABLE)])
+def test_order_sharded_analysis_is_a_disjoint_partition(engine, nmax, B, flags):
+    """m-order sharding (shb200_plan_set_order_shard): the `world` shards are disjoint and their sum is bit-identical to the
+    unsharded analysis -- what the multi-GPU planner relies on when it gathers with all_reduce(SUM)."""
+    g = sb.lonlat_grid(nmax, gtype="regular_lon0")
+    f = np.random.default_rng(8).standard_normal((B, len(g["lat"]), len(g["lon"])))
+    full = engine.analysis(f, nmax, g["lon"], g["lat"], flags=flags)
+    n, m = sb.nm_index(nmax)
+    for world in (2, 3, 8):
+        acc = np.zeros_like(full)
+        for rank in range(world):
+            part = engine.analysis(f, nmax, g["lon"], g["lat"], flags=flags, order_shard=(rank, world))
+            mine = (np.abs(m) % world) == rank
+            assert np.all(part[:, ~mine] == 0.0)
+            assert np.array_equal(part[:, mine], full[:, mine])
+            acc += part
+        assert np.array_equal(acc, full)
+    again = engine.analysis(f, nmax, g["lon"], g["lat"], flags=flags)      # shard switched off again
+    assert np.array_equal(again, full)
