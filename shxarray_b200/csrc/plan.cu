@@ -159,6 +159,10 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
     }
     p.nrows = (int)i1.size();
     const int R = p.nrows;
+    if (d.quadrature != SHB200_QUAD_NONE && R > 8192) {
+        set_error("plan_create: analysis supports at most 8192 distinct latitude rows (recursion state is kept in shared memory)");
+        return SHB200_EUNSUPPORTED;
+    }
     std::vector<double> cost(R), w1(R, 0.0), w2(R, 0.0);
     for (int r = 0; r < R; ++r) cost[r] = cost_lat[i1[r]];
     if (d.quadrature != SHB200_QUAD_NONE) {

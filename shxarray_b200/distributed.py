@@ -28,9 +28,21 @@ def shard_bounds(total, world, rank):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+_shard_cache = {}
+
+
 def lat_shard_indices(lat, world, rank):
     """Latitude indices owned by ``rank``: mirror pairs (lat, -lat) are kept together, unpaired rows are dealt last."""
     lat = np.asarray(lat, dtype=np.float64)
+    key = (lat.tobytes(), int(world))
+    if key not in _shard_cache:
+        if len(_shard_cache) > 8:
+            _shard_cache.clear()
+        _shard_cache[key] = [_lat_shard_indices(lat, world, r) for r in range(world)]
+    return _shard_cache[key][rank]
+
+
+def _lat_shard_indices(lat, world, rank):
     L = len(lat)
     used = np.zeros(L, dtype=bool)
     where = {}
