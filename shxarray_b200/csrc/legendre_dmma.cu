@@ -108,10 +108,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_leg_syn_dmma(DevTables t, const
             for (int g = 0; g < 4; ++g)
 #pragma unroll
                 for (int cb = 0; cb < 4; ++cb) { acc[e][g][cb][0] = 0.0; acc[e][g][cb][1] = 0.0; }
+        int prev = -1;   // deferred release: see legendre_tab.cu (an arrive may be scheduled ahead of a stage's last fragment loads)
         for (int ch = 0; ch < nchunks; ++ch) {
             const int s = ch % STAGES;
             const uint32_t ph = (ch / STAGES) & 1;
             mbar_wait(&full[s], ph);
+            if (prev >= 0) { __syncwarp(); if (lane == 0) mbar_arrive(&empty[prev]); }
+            prev = s;
             const Stage& S = st[s];
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks)
@@ -128,8 +131,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_leg_syn_dmma(DevTables t, const
 #pragma unroll
                         for (int cb = 0; cb < 4; ++cb) dmma(acc[e][g][cb][0], acc[e][g][cb][1], A[g], B[cb]);
                 }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
         }
         // epilogue: store E/O
 #pragma unroll
@@ -169,9 +170,12 @@ constexpr int SB = 128;           // degrees per super-block
 constexpr int NCOLS = 128;
 constexpr int PROW = RT + 2;      // 272 B = 16 mod 64
 constexpr int CROW = NCOLS + 2;
-constexpr int PSTAGES = 4;
+constexpr int PSTAGES = 8;       // = 2 producer warps x SB/NS stages: row tile `it` uses stages (it&1)*4 + inner, so every stage barrier
+                                 // has ONE producer warp.  With a shared 4-stage ring the warp that finished tile `it` could reach the
+                                 // "stage empty" wait of tile it+2 while the barrier was still in phase `it`; a parity wait cannot tell
+                                 // phase it from it+2 and let it through (intermittent corruption / launch failure, found by stress runs).
 constexpr int NCONS = 256, NPROD = 64, NTHREADS = NCONS + NPROD;
-constexpr int MAXROWS = 2048;     // recursion state kept in shared memory
+constexpr int MAXROWS = 1280;     // recursion state kept in shared memory
 
 struct __align__(16) GTile { double g[RT][2][CROW]; };
 struct __align__(16) PTile { double p[NS][PROW]; };
@@ -265,6 +269,7 @@ __global__ void __launch_bounds__(ana::NTHREADS, 1) k_leg_ana_dmma(DevTables t, 
         const int e = warp & 1, cq = warp >> 1;
         const int lr = lane >> 2, lk = lane & 3;
         double acc[8][4][2];
+        int prev_s = -1, prev_g = -1;   // deferred release (see legendre_tab.cu)
         for (int sb = 0; sb < nsb; ++sb) {
 #pragma unroll
             for (int nb = 0; nb < 8; ++nb)
@@ -274,12 +279,16 @@ __global__ void __launch_bounds__(ana::NTHREADS, 1) k_leg_ana_dmma(DevTables t, 
                 const int it = sb * nrt + rt;
                 const int gb = it & 1;
                 mbar_wait(&gfull[gb], (it >> 1) & 1);
+                if (prev_g >= 0) { __syncwarp(); if (lane == 0) mbar_arrive(&gempty[prev_g]); }
+                prev_g = gb;
                 const GTile& GT = gt[gb];
 #pragma unroll
                 for (int inner = 0; inner < SB / NS; ++inner) {
                     const int sidx = it * (SB / NS) + inner;
                     const int s = sidx % PSTAGES;
                     mbar_wait(&pfull[s], (sidx / PSTAGES) & 1);
+                    if (prev_s >= 0) { __syncwarp(); if (lane == 0) mbar_arrive(&pempty[prev_s]); }
+                    prev_s = s;
                     const PTile& PT = ptile[s];
 #pragma unroll
                     for (int ks = 0; ks < RT / 4; ++ks) {
@@ -293,10 +302,7 @@ __global__ void __launch_bounds__(ana::NTHREADS, 1) k_leg_ana_dmma(DevTables t, 
 #pragma unroll
                             for (int cb = 0; cb < 4; ++cb) dmma(acc[2 * inner + q][cb][0], acc[2 * inner + q][cb][1], A[q], B[cb]);
                     }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&pempty[s]);
                 }
-                if (lane == 0) mbar_arrive(&gempty[gb]);
             }
             // store the finished super-block
 #pragma unroll

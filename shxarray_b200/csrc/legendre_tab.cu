@@ -19,6 +19,8 @@
 // One TMA warp (elected lane issues cp.async.bulk row copies into padded shared-memory tiles, mbarrier
 // complete_tx) + 8 consumer warps (64 DMMA.8x8x4 per stage each), full/empty mbarrier ring.
 // Plans whose table would not fit the budget fall back to the fused on-the-fly kernels.
+#include <algorithm>
+
 #include "internal.h"
 #include "recursion.cuh"
 #include "dmma_common.cuh"
@@ -62,21 +64,23 @@ struct __align__(16) Stage {
 constexpr size_t SMEM = sizeof(Stage) * STAGES + 2 * STAGES * sizeof(uint64_t);
 }  // namespace ts
 
+// Persistent: gridDim.x CTAs (one per SM) walk the (order, row-tile) list in snake order -- tile k*P + c on even
+// rounds, k*P + P-1-c on odd rounds; orders ascend, so work descends and every CTA gets the same total -- and the TMA
+// warp keeps filling the ring across tile boundaries, so the tensor pipe does not drain 29 times per SM per launch.
 __global__ void __launch_bounds__(ts::NTHREADS, 1) k_leg_syn_tab(DevTables t, const double* __restrict__ Ptab, const double* __restrict__ Cm,
-                                                                  double* __restrict__ G) {
+                                                                  double* __restrict__ G, int nrt, int ntiles) {
     using namespace ts;
     extern __shared__ __align__(128) unsigned char smraw[];
     Stage* st = reinterpret_cast<Stage*>(smraw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smraw + sizeof(Stage) * STAGES);
     uint64_t* empty = full + STAGES;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m = blockIdx.y, row0 = blockIdx.x * TR, col0 = blockIdx.z * NCOLS;
+    const int col0 = blockIdx.y * NCOLS;
     const int N = t.nmax, R = t.nrows, NC = t.NC;
     const int ncols = min(NCOLS, NC - col0);
-    const int nchunks = (N - m + CH) / CH;
-    const int64_t tmm = tri(m, m, N);
     const bool onecopy = NC <= NCOLS;                  // whole rows of Cm fit the tile: contiguous block, padded stride Cs
     const int crow = onecopy ? t.Cs : CROW;
+    const int P = gridDim.x, c = blockIdx.x;
 
     // no zero fill: degrees beyond nmax have P = 0 in the table and the Cm rows fetched with them are finite
     if (tid == 0) {
@@ -91,72 +95,93 @@ __global__ void __launch_bounds__(ts::NTHREADS, 1) k_leg_syn_tab(DevTables t, co
 
     if (warp == NCONS / 32) {
         // ------------------------------------------------------------------ TMA warp
-        const double* psrc = Ptab + (t.pt_base[m] * t.RT32 + 2 * blockIdx.x) * PT_SUB;
-        for (int ch = 0; ch < nchunks; ++ch) {
-            const int s = ch % STAGES;
-            mbar_wait(&empty[s], ((ch / STAGES) & 1) ^ 1);
-            const int k0 = ch * CH;
-            if (onecopy) {
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(&full[s], (uint32_t)((2 * PT_SUB + CH * crow) * 8));
-                    bulk_g2s(&st[s].P[0], psrc + (int64_t)ch * t.RT32 * PT_SUB, 2 * PT_SUB * 8, &full[s]);
-                    bulk_g2s(&st[s].C[0], Cm + (tmm + k0) * t.Cs, (uint32_t)(CH * crow * 8), &full[s]);
+        int gc = 0;                                     // chunks issued so far (ring position)
+        for (int rnd = 0;; ++rnd) {
+            const int tile = rnd * P + ((rnd & 1) ? P - 1 - c : c);
+            if (tile >= ntiles) { if (rnd * P >= ntiles) break; else continue; }
+            const int m = tile / nrt, rt = tile - m * nrt;
+            const int nchunks = (N - m + CH) / CH;
+            const int64_t tmm = tri(m, m, N);
+            const double* psrc = Ptab + (t.pt_base[m] * t.RT32 + 2 * rt) * PT_SUB;
+            for (int ch = 0; ch < nchunks; ++ch, ++gc) {
+                const int s = gc % STAGES;
+                mbar_wait(&empty[s], ((gc / STAGES) & 1) ^ 1);
+                const int k0 = ch * CH;
+                if (onecopy) {
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(&full[s], (uint32_t)((2 * PT_SUB + CH * crow) * 8));
+                        bulk_g2s(&st[s].P[0], psrc + (int64_t)ch * t.RT32 * PT_SUB, 2 * PT_SUB * 8, &full[s]);
+                        bulk_g2s(&st[s].C[0], Cm + (tmm + k0) * t.Cs, (uint32_t)(CH * crow * 8), &full[s]);
+                    }
+                } else {
+                    const int valid = min(CH, N - m - k0 + 1);
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(&full[s], (uint32_t)(2 * PT_SUB * 8 + valid * ncols * 8));
+                        bulk_g2s(&st[s].P[0], psrc + (int64_t)ch * t.RT32 * PT_SUB, 2 * PT_SUB * 8, &full[s]);
+                        for (int j = 0; j < valid; ++j)
+                            bulk_g2s(&st[s].C[j * crow], Cm + (tmm + k0 + j) * t.Cs + col0, (uint32_t)(ncols * 8), &full[s]);
+                    }
                 }
-            } else {
-                const int valid = min(CH, N - m - k0 + 1);
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(&full[s], (uint32_t)(2 * PT_SUB * 8 + valid * ncols * 8));
-                    bulk_g2s(&st[s].P[0], psrc + (int64_t)ch * t.RT32 * PT_SUB, 2 * PT_SUB * 8, &full[s]);
-                }
-                __syncwarp();
-                if (lane < valid) bulk_g2s(&st[s].C[lane * crow], Cm + (tmm + k0 + lane) * t.Cs + col0, (uint32_t)(ncols * 8), &full[s]);
             }
         }
     } else {
         // ------------------------------------------------------------------ consumers
         const int wr = warp >> 2, wc = warp & 3;
         const int lr = lane >> 2, lk = lane & 3;
-        double acc[2][4][4][2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e)
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-#pragma unroll
-                for (int cb = 0; cb < 4; ++cb) { acc[e][g][cb][0] = 0.0; acc[e][g][cb][1] = 0.0; }
-        for (int ch = 0; ch < nchunks; ++ch) {
-            const int s = ch % STAGES;
-            mbar_wait(&full[s], (ch / STAGES) & 1);
-            const double* __restrict__ SP = st[s].P + wr * PT_SUB + lr;
-            const double* __restrict__ SC = st[s].C + 32 * wc + lr;
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int j = 8 * ks + 2 * lk + e;
-                    double A[4], B[4];
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) A[g] = SP[j * 34 + 8 * g];
-#pragma unroll
-                    for (int cb = 0; cb < 4; ++cb) B[cb] = SC[j * crow + 8 * cb];
-#pragma unroll
-                    for (int g = 0; g < 4; ++g)
-#pragma unroll
-                        for (int cb = 0; cb < 4; ++cb) dmma(acc[e][g][cb][0], acc[e][g][cb][1], A[g], B[cb]);
-                }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            const int row = row0 + 32 * wr + 8 * g + lr;
-            if (row >= R) continue;
+        int gc = 0;
+        int prev = -1;      // stage whose fragments were consumed last; released only after the NEXT stage has been acquired
+        for (int rnd = 0;; ++rnd) {
+            const int tile = rnd * P + ((rnd & 1) ? P - 1 - c : c);
+            if (tile >= ntiles) { if (rnd * P >= ntiles) break; else continue; }
+            const int m = tile / nrt, rt = tile - m * nrt;
+            const int nchunks = (N - m + CH) / CH;
+            const int row0 = rt * TR;
+            double acc[2][4][4][2];
 #pragma unroll
             for (int e = 0; e < 2; ++e)
 #pragma unroll
-                for (int cb = 0; cb < 4; ++cb) {
-                    const int col = col0 + 32 * wc + 8 * cb + 2 * lk;
-                    if (col < NC) *reinterpret_cast<double2*>(G + (((int64_t)m * R + row) * 2 + e) * t.Gs + col) = make_double2(acc[e][g][cb][0], acc[e][g][cb][1]);
-                }
+                for (int g = 0; g < 4; ++g)
+#pragma unroll
+                    for (int cb = 0; cb < 4; ++cb) { acc[e][g][cb][0] = 0.0; acc[e][g][cb][1] = 0.0; }
+            for (int ch = 0; ch < nchunks; ++ch, ++gc) {
+                const int s = gc % STAGES;
+                mbar_wait(&full[s], (gc / STAGES) & 1);
+                // Release of the previous stage is deferred to here: ptxas is free to schedule an mbarrier arrive ahead of
+                // the last DMMAs of a stage, i.e. while their LDS operands are still in flight (observed: the TMA refill
+                // then raced with the slowest warps' last fragment loads).  After this wait, every load of stage `prev`
+                // has been consumed by DMMAs issued in the previous loop iteration.
+                if (prev >= 0) { __syncwarp(); if (lane == 0) mbar_arrive(&empty[prev]); }
+                prev = s;
+                const double* __restrict__ SP = st[s].P + wr * PT_SUB + lr;
+                const double* __restrict__ SC = st[s].C + 32 * wc + lr;
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int j = 8 * ks + 2 * lk + e;
+                        double A[4], B[4];
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) A[g] = SP[j * 34 + 8 * g];
+#pragma unroll
+                        for (int cb = 0; cb < 4; ++cb) B[cb] = SC[j * crow + 8 * cb];
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)
+#pragma unroll
+                            for (int cb = 0; cb < 4; ++cb) dmma(acc[e][g][cb][0], acc[e][g][cb][1], A[g], B[cb]);
+                    }
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int row = row0 + 32 * wr + 8 * g + lr;
+                if (row >= R) continue;
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+#pragma unroll
+                    for (int cb = 0; cb < 4; ++cb) {
+                        const int col = col0 + 32 * wc + 8 * cb + 2 * lk;
+                        if (col < NC) *reinterpret_cast<double2*>(G + (((int64_t)m * R + row) * 2 + e) * t.Gs + col) = make_double2(acc[e][g][cb][0], acc[e][g][cb][1]);
+                    }
+            }
         }
     }
 }
@@ -237,6 +262,7 @@ __global__ void __launch_bounds__(ta::NTHREADS, 1) k_leg_ana_tab(DevTables t, co
         const int lr = lane >> 2, lk = lane & 3;
         double acc[8][4][2];
         int sidx = 0;
+        int prev_s = -1, prev_g = -1;   // P stage / G buffer consumed last: released after the next one has been acquired (see k_leg_syn_tab)
         for (int sb = 0; sb < nsb; ++sb) {
             const int ninner = min(SB / NS, (N - m - sb * SB + NS) / NS);
 #pragma unroll
@@ -248,6 +274,8 @@ __global__ void __launch_bounds__(ta::NTHREADS, 1) k_leg_ana_tab(DevTables t, co
                 const int gb = it & 1;
                 const int nr = min(RT, R - rt * RT);
                 mbar_wait(&gfull[gb], (it >> 1) & 1);
+                if (prev_g >= 0) { __syncwarp(); if (lane == 0) mbar_arrive(&gempty[prev_g]); }
+                prev_g = gb;
                 const double* __restrict__ GT = gt[gb].g + e * grow + 32 * cq + lr;
 #pragma unroll
                 for (int inner = 0; inner < SB / NS; ++inner) {
@@ -255,8 +283,12 @@ __global__ void __launch_bounds__(ta::NTHREADS, 1) k_leg_ana_tab(DevTables t, co
                     const int s = sidx % PSTAGES;
                     mbar_wait(&pfull[s], (sidx / PSTAGES) & 1);
                     ++sidx;
+                    if (prev_s >= 0) { __syncwarp(); if (lane == 0) mbar_arrive(&pempty[prev_s]); }
+                    prev_s = s;
                     const double* __restrict__ PT = ptile[s].p + (2 * lr + e) * 34 + lk;
                     const bool two = (N - m - (sb * SB + inner * NS) + 1) > 16;     // second 16-degree block present
+                    // (skipping the k-steps past the last latitude row of the final tile saves 5 % of the DMMAs but the
+                    //  conditional exit costs the straight-line schedule 9 %: measured, not kept)
 #pragma unroll
                     for (int ks = 0; ks < RT / 4; ++ks) {
                         double A[2], B[4];
@@ -271,10 +303,7 @@ __global__ void __launch_bounds__(ta::NTHREADS, 1) k_leg_ana_tab(DevTables t, co
 #pragma unroll
                             for (int cb = 0; cb < 4; ++cb) dmma(acc[2 * inner + q][cb][0], acc[2 * inner + q][cb][1], A[q], B[cb]);
                     }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&pempty[s]);
                 }
-                if (lane == 0) mbar_arrive(&gempty[gb]);
             }
 #pragma unroll
             for (int nb = 0; nb < 8; ++nb) {
@@ -297,8 +326,12 @@ bool launch_legendre_syn_tab(const Plan& p, cudaStream_t st) {
         if (cudaFuncSetAttribute(k_leg_syn_tab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts::SMEM) != cudaSuccess) return false;
         attr = true;
     }
-    dim3 grid((p.nrows + ts::TR - 1) / ts::TR, p.nmax + 1, (p.NC + ts::NCOLS - 1) / ts::NCOLS);
-    k_leg_syn_tab<<<grid, ts::NTHREADS, ts::SMEM, st>>>(p.t, p.Ptab, p.Cm, p.G);
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int nrt = (p.nrows + ts::TR - 1) / ts::TR, ntiles = nrt * (p.nmax + 1);
+    const int ncolt = (p.NC + ts::NCOLS - 1) / ts::NCOLS;
+    dim3 grid(std::max(1, std::min(ntiles, sms / std::min(ncolt, sms))), ncolt);
+    k_leg_syn_tab<<<grid, ts::NTHREADS, ts::SMEM, st>>>(p.t, p.Ptab, p.Cm, p.G, nrt, ntiles);
     return true;
 }
 

@@ -14,8 +14,6 @@
 // digit-reversed slot, natural-order output -> coalesced row stores), decimation in frequency for analysis (natural
 // input, spectrum picked up from the digit-reversed slots).  NF consecutive fields of one latitude pair per CTA so that
 // every G access is a full 64 B segment.
-#include <cstdlib>
-
 #include "internal.h"
 
 namespace shb {
@@ -316,7 +314,7 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_ana_fft(DevTables t, Params 
                 const int kc = k ? K - k : 0;
                 const int kcur = k;
                 k += kstep; if (k >= K) k -= K;
-                if (m < t.m0 || (m - t.m0) % t.mstride) continue;          // order integrated on another rank (m-sharding)
+                if (t.mstride > 1 && (m < t.m0 || (m - t.m0) % t.mstride)) continue;   // order integrated on another rank (m-sharding)
                 const double2 Wk = xx[padi(perm[kcur])], Wc = cconj(xx[padi(perm[kc])]);
                 const double2 F = make_double2(0.5 * (Wk.x + Wc.x), 0.5 * (Wk.y + Wc.y));      // spectrum of the primary row
                 const double2 D = csub(Wk, Wc);
@@ -355,10 +353,6 @@ static bool fft_params(int K, int Bp, fft::Params& fp) {
     for (int c = 1; c <= 8 && c <= Bp; c *= 2)
         if (c * per <= 220 * 1024) nf = c;
     if (nf == 0) return false;
-    {
-        const char* e = getenv("SHB200_FFT_NF");
-        if (e && atoi(e) > 0 && atoi(e) < nf) nf = atoi(e);
-    }
     fp.NF = nf;
     fp.TPT = nf >= 4 ? 64 : (nf == 2 ? 128 : 256);
     fp.nthreads = fp.NF * fp.TPT;
