@@ -39,8 +39,14 @@ def run(tag, nmax, B, gtype, quad, flags=0, lon=None, lat=None, lw=None, weight=
     plans = list(eng._plans.values())
     info = {("ana" if p.info.launches_analysis and p is plans[-1] else "syn"): (p.info.dmma, p.info.lon_fft, p.info.nrows) for p in plans}
     err = float(((a - c).abs().amax(dim=1) / c.abs().amax(dim=1)).max())
+    stages = {}
+    for pl in plans:
+        try:
+            stages.update({k: round(v, 4) for k, v in pl.stage_times().items() if v > 0})
+        except Exception:
+            pass
     res = dict(config=tag, nmax=nmax, batch=B, grid=[len(lat), len(lon)], synthesis_ms=t_s, analysis_ms=t_a,
-               fields_per_s_roundtrip=B / ((t_s + t_a) * 1e-3), roundtrip_rel_err=err, kernels=str(info))
+               fields_per_s_roundtrip=B / ((t_s + t_a) * 1e-3), roundtrip_rel_err=err, kernels=str(info), stages_ms=stages)
     print(json.dumps(res), flush=True)
     eng.clear()
     return res
