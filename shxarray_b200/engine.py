@@ -10,6 +10,7 @@ device in one call (the per-field Python loop of shtns.py:255-259 is what this e
 """
 import hashlib
 import threading
+from collections import OrderedDict
 
 import numpy as np
 
@@ -157,11 +158,14 @@ class SHEngine:
 
     #: device memory budget for one plan's workspace (bytes); larger batches are processed in chunks
     WORKSPACE_BUDGET = 48 << 30
+    #: the plan cache is LRU: at most MAX_PLANS plans and CACHE_BUDGET bytes of device workspace stay alive
+    MAX_PLANS = 12
+    CACHE_BUDGET = 64 << 30
 
     def __init__(self, device=0, flags=0):
         self.device = int(device)
         self.flags = int(flags)
-        self._plans = {}
+        self._plans = OrderedDict()
         self._lock = threading.Lock()
         self.launches = 0   # kernels launched by this engine (gpu_launches accounting in bench.py)
 
@@ -179,12 +183,20 @@ class SHEngine:
         with self._lock:
             plan = self._plans.get(key)
             if plan is not None and plan.max_batch >= maxb:
+                self._plans.move_to_end(key)
                 return plan
             if plan is not None:
+                del self._plans[key]
                 plan.close()
             plan = capi.Plan(nmax, lat, lon, max_batch=maxb, n=n, m=m, mode=mode, quadrature=quadrature,
                              weight=weight, lat_weights=lat_weights, flags=flags, device=self.device)
             self._plans[key] = plan
+            # least-recently-used eviction (a plan owns its workspace and, for tensor-core plans, a P_nm table)
+            total = sum(int(q.info.workspace_bytes) for q in self._plans.values())
+            while len(self._plans) > 3 and (len(self._plans) > self.MAX_PLANS or total > self.CACHE_BUDGET):   # multiply() holds 3 plans
+                _, old = self._plans.popitem(last=False)
+                total -= int(old.info.workspace_bytes)
+                old.close()
             return plan
 
     def clear(self):
