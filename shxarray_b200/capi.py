@@ -58,6 +58,12 @@ def lib():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
+        # a clean checkout: compile the CUDA library in-tree once (nvcc, sm_100a); still no fallback if that fails
+        import shutil
+        import subprocess
+        if shutil.which("make") and (shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc")):
+            subprocess.run(["make", "-s", "-j8", "-C", os.path.join(_HERE, "csrc")], check=False)
+    if not os.path.exists(LIB_PATH):
         raise SHB200Error(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                           "or `make -C shxarray_b200/csrc` (the engine has no CPU fallback)")
     L = C.CDLL(LIB_PATH)
