@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_syn_fft(DevTables t, Params 
     for (int rnd = 0; rnd < nrounds; ++rnd) {
         const int mlo = rnd * K, mhi = min(N, mlo + K - 1);
         for (int sub = 0; sub < (simple ? 1 : 2); ++sub) {
-            constexpr int UN = 4;                       // independent orders in flight per thread
+            constexpr int UN = 4;                       // independent orders in flight per thread (6 spills at the 128-register cap and is slower)
             for (int m0 = mlo + (tid >> fsh); m0 <= mhi; m0 += mstep * UN) {
                 double Ec[UN], Es[UN], Oc[UN], Os[UN];
                 double2 ph[UN];
@@ -278,11 +278,27 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_ana_fft(DevTables t, Params 
         const double* f1 = grid + (int64_t)b * gs_b + (int64_t)i1 * gs_lat;
         const double* f2 = grid + (int64_t)b * gs_b + (int64_t)(mirror ? i2 : 0) * gs_lat;
         if (live && gs_lon == 1 && (K & 1) == 0 && ((reinterpret_cast<uintptr_t>(f1) | reinterpret_cast<uintptr_t>(f2)) & 15) == 0) {
-            for (int j = 2 * lt; j < K; j += 2 * fp.TPT) {          // two longitudes per thread: 16-byte row loads
-                const double2 a = *reinterpret_cast<const double2*>(f1 + j);
-                const double2 c = mirror ? *reinterpret_cast<const double2*>(f2 + j) : make_double2(0.0, 0.0);
-                x[padi(j)] = make_double2(a.x, c.x);
-                x[padi(j + 1)] = make_double2(a.y, c.y);
+            // two longitudes per thread per load (16-byte row loads), 6 iterations' loads in flight before the first use:
+            // this phase is pure DRAM latency (ncu r01: 38 % of the kernel's samples, all long-scoreboard)
+            constexpr int UL = 6;
+            for (int j0 = 2 * lt; j0 < K; j0 += 2 * fp.TPT * UL) {
+                double2 a[UL], c[UL];
+#pragma unroll
+                for (int u = 0; u < UL; ++u) {
+                    const int j = j0 + u * 2 * fp.TPT;
+                    if (j < K) {
+                        a[u] = *reinterpret_cast<const double2*>(f1 + j);
+                        c[u] = mirror ? *reinterpret_cast<const double2*>(f2 + j) : make_double2(0.0, 0.0);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UL; ++u) {
+                    const int j = j0 + u * 2 * fp.TPT;
+                    if (j < K) {
+                        x[padi(j)] = make_double2(a[u].x, c[u].x);
+                        x[padi(j + 1)] = make_double2(a[u].y, c[u].y);
+                    }
+                }
             }
         } else {
             for (int j = lt; j < K; j += fp.TPT) {
@@ -310,6 +326,7 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_ana_fft(DevTables t, Params 
             double* gcol = G + ((int64_t)row * 2) * t.Gs + colidx(0, b, t.GS);
             int k = (tid >> fsh) % K;
             const int kstep = mstep % K;
+#pragma unroll 4
             for (int m = tid >> fsh; m <= N; m += mstep) {
                 const int kc = k ? K - k : 0;
                 const int kcur = k;
