@@ -287,21 +287,28 @@ __global__ void __launch_bounds__(ta::NTHREADS, 1) k_leg_ana_tab(DevTables t, co
                     prev_s = s;
                     const double* __restrict__ PT = ptile[s].p + (2 * lr + e) * 34 + lk;
                     const bool two = (N - m - (sb * SB + inner * NS) + 1) > 16;     // second 16-degree block present
-                    // (skipping the k-steps past the last latitude row of the final tile saves 5 % of the DMMAs but the
-                    //  conditional exit costs the straight-line schedule 9 %: measured, not kept)
-#pragma unroll
-                    for (int ks = 0; ks < RT / 4; ++ks) {
+                    auto kstep = [&](int ks, bool rowok) {
                         double A[2], B[4];
                         A[0] = PT[4 * ks];
                         A[1] = two ? PT[PT_SUB + 4 * ks] : 0.0;
-#pragma unroll
-                        const bool rowok = 4 * ks + lk < nr;        // rows past the last latitude were never copied
 #pragma unroll
                         for (int cb = 0; cb < 4; ++cb) B[cb] = rowok ? GT[(4 * ks + lk) * 2 * grow + 8 * cb] : 0.0;
 #pragma unroll
                         for (int q = 0; q < 2; ++q)
 #pragma unroll
                             for (int cb = 0; cb < 4; ++cb) dmma(acc[2 * inner + q][cb][0], acc[2 * inner + q][cb][1], A[q], B[cb]);
+                    };
+                    if (nr == RT) {
+                        // full tile: straight-line schedule of all 8 k-steps
+#pragma unroll
+                        for (int ks = 0; ks < RT / 4; ++ks) kstep(ks, true);
+                    } else {
+                        // last tile of the latitude range: only the k-steps (4 rows each) that hold rows; rows past the last
+                        // latitude were never copied.  A separate rolled loop: an early exit inside the unrolled loop above cost
+                        // the full tiles 9 % (measured)
+                        const int kmax = (nr + 3) >> 2;
+#pragma unroll 1
+                        for (int ks = 0; ks < kmax; ++ks) kstep(ks, 4 * ks + lk < nr);
                     }
                 }
             }
