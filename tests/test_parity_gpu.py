@@ -409,3 +409,33 @@ def test_repeated_transforms_are_deterministic(engine, nmax, B, flags):
         a = engine.analysis(f0, nmax, g["lon"], g["lat"], flags=flags)
         assert torch.equal(f, f0)
         assert torch.equal(a, a0)
+
+
+def test_batch_chunking_and_strided_device_views(engine):
+    """A batch larger than one plan's workspace budget is processed in chunks; torch views with arbitrary strides go
+    straight to the C ABI (the reference reshapes non-contiguous views by copying: synthesis.pyx:104-118)."""
+    import torch
+    nmax, B = 48, 23
+    g = sb.lonlat_grid(nmax, gtype="regular")
+    c = S.random_coefficients(nmax, B, kaula=False, seed=41)
+    ref = engine.synthesis(c, lon=g["lon"], lat=g["lat"], nmax=nmax)
+    small = sb.SHEngine(device=0)
+    per_field = 16 * (nmax + 1) * (nmax + 2) // 2 + 32 * (nmax + 1) * len(g["lat"])
+    small.WORKSPACE_BUDGET = per_field * 5          # -> chunks of 5 fields
+    out = small.synthesis(c, lon=g["lon"], lat=g["lat"], nmax=nmax)
+    assert np.array_equal(out, ref)
+    back = small.analysis(out, nmax, g["lon"], g["lat"])
+    full = engine.analysis(ref, nmax, g["lon"], g["lat"])
+    # 5-field chunks run the tiny-batch kernels (different summation order over latitudes than the tensor-core path)
+    assert per_field_err(back, full) <= 1e-13
+    small.clear()
+    # device tensors: nm-first storage seen through a transposed view, and a strided batch slice
+    ct = torch.from_numpy(np.ascontiguousarray(c.T)).cuda()          # [nsh, B]
+    out_t = engine.synthesis(ct.T, lon=g["lon"], lat=g["lat"], nmax=nmax)
+    assert np.array_equal(out_t.cpu().numpy(), ref)
+    big = torch.from_numpy(np.repeat(c, 2, axis=0)).cuda()           # every field twice
+    out_s = engine.synthesis(big[::2], lon=g["lon"], lat=g["lat"], nmax=nmax)
+    assert np.array_equal(out_s.cpu().numpy(), ref)
+    gt = torch.from_numpy(ref).cuda().permute(1, 2, 0).contiguous().permute(2, 0, 1)   # [B, lat, lon] view of [lat, lon, B] storage
+    a_view = engine.analysis(gt, nmax, g["lon"], g["lat"])
+    assert np.array_equal(a_view.cpu().numpy(), engine.analysis(ref, nmax, g["lon"], g["lat"]))
