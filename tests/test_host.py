@@ -86,3 +86,20 @@ def test_analysis_weight_expression():
     w = sb.analysis_weight_shlib(lon, lat)
     stepx = 0.5 * np.pi / 180
     assert w == abs(stepx * stepx) / (4 * np.pi)
+
+
+def test_c_abi_from_plain_c(tmp_path):
+    """include/shb200.h is valid C and the library is callable from a C program without python/torch."""
+    import shutil
+    import subprocess
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    capi.lib()
+    exe = str(tmp_path / "cabi_smoke")
+    libdir = os.path.dirname(capi.LIB_PATH)
+    subprocess.check_call([cc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cabi_smoke.c"),
+                           "-o", exe, "-L", libdir, "-lshb200", "-lm", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert out.stdout.startswith(("no-gpu", "gpu: ok"))

@@ -439,3 +439,19 @@ def test_batch_chunking_and_strided_device_views(engine):
     gt = torch.from_numpy(ref).cuda().permute(1, 2, 0).contiguous().permute(2, 0, 1)   # [B, lat, lon] view of [lat, lon, B] storage
     a_view = engine.analysis(gt, nmax, g["lon"], g["lat"])
     assert np.array_equal(a_view.cpu().numpy(), engine.analysis(ref, nmax, g["lon"], g["lat"]))
+
+
+def test_c_abi_transform_from_plain_c(tmp_path):
+    """The same C program as tests/test_host.py::test_c_abi_from_plain_c, on a GPU: plan_create + synthesis_host from C."""
+    import shutil
+    import subprocess
+    from conftest import ROOT
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    exe = str(tmp_path / "cabi_smoke")
+    libdir = os.path.dirname(capi.LIB_PATH)
+    subprocess.check_call([cc, "-std=c99", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cabi_smoke.c"),
+                           "-o", exe, "-L", libdir, "-lshb200", "-lm", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("gpu: ok"), (out.returncode, out.stdout, out.stderr)
