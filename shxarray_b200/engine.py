@@ -40,7 +40,7 @@ def lonlat_grid(nmax=None, lon=None, lat=None, gtype=None):
     Gauss-Legendre grid (nlat = nmax+1 rounded up to a multiple of 4, nlon FFT-friendly >= 2nmax+2).
     Returns dict(lon=, lat=, gtype=, lat_weights= (gauss only))."""
     if gtype is None:
-        gtype = "gauss"
+        gtype = "gauss" if nmax is not None else "regular"
     if gtype not in ("regular", "regular_lon0", "gauss", "point"):
         raise ValueError("Only 'gauss', 'regular', 'regular_lon0' and 'point' grid types are supported")
     if nmax is not None:

@@ -58,7 +58,8 @@ class B200Backend(SHComputeBackendBase):
         """Create a lon/lat grid for this backend.  gtype: 'gauss' (default), 'regular', 'regular_lon0' (identical to
         shlib.pyx:87-96) or 'point'.  Sets ``shxarray_gtype`` on both coordinates (shlib.pyx:115-116)."""
         if gtype is None:
-            gtype = "gauss"
+            # generated grids default to Gauss-Legendre; user-supplied lon/lat are labelled like shlib does (shlib.pyx:76-77)
+            gtype = "gauss" if nmax is not None else "regular"
         if lon is not None and hasattr(lon, "data"):
             lon = lon.data
         if lat is not None and hasattr(lat, "data"):
