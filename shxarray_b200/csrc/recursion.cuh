@@ -42,6 +42,23 @@ struct LegExact {
         ++n;
         return val;
     }
+    // same step with the table entries passed by value: wk = wnm(n, m), wkm1 = wnm(n-1, m), rkm1 = RN(1 / wnm(n-1, m))
+    __device__ __forceinline__ double next_v(double wk, double wkm1, double rkm1, double pmm) {
+        const int k = n - m;
+        double val;
+        if (k == 0) {
+            val = pmm;
+        } else if (k == 1) {
+            p1 = __dmul_rn(__dmul_rn(wk, c), p2);
+            val = __dmul_rn(p1, sect);
+        } else {
+            const double pn = leg_step(c, p1, p2, wk, wkm1, rkm1);
+            val = __dmul_rn(pn, sect);
+            p2 = p1; p1 = pn;
+        }
+        ++n;
+        return val;
+    }
 };
 
 }  // namespace shb

@@ -53,16 +53,25 @@ def run(tag, nmax, B, gtype, quad, flags=0, lon=None, lat=None, lw=None, weight=
 
 
 if __name__ == "__main__":
+    only = sys.argv[1:]                 # optional substrings: run only the configs whose tag contains one of them
     out = []
-    out.append(run("cfg1 nmax60 shlib 1deg B=1", 60, 1, "regular", "shlib"))
-    out.append(run("cfg2 nmax96 0.5deg B=240", 96, 240, "regular", "shlib"))
-    out.append(run("cfg5 nmax256 gauss B=4", 256, 4, "gauss", "gauss"))
-    out.append(run("cfg3 nmax720 gauss B=64", 720, 64, "gauss", "gauss"))
+
+    def add(tag, *a, **k):
+        if not only or any(o in tag for o in only):
+            out.append(run(tag, *a, **k))
+
+    add("cfg1 nmax60 shlib 1deg B=1", 60, 1, "regular", "shlib")
+    add("cfg2 nmax96 0.5deg B=240", 96, 240, "regular", "shlib")
+    add("cfg5 nmax256 gauss B=4", 256, 4, "gauss", "gauss")
+    add("cfg3 nmax720 gauss B=64", 720, 64, "gauss", "gauss")
     d = 1.0 / 12
     h = np.arange(d / 2, 90, d)
     lat = np.concatenate([-h[::-1], h])          # bit-exact mirror symmetry (np.arange(-90+d/2, 90, d) is off by ulps for d=1/12)
     lon = np.arange(0, 360, d)
     w = (d * np.pi / 180) ** 2 / (4 * np.pi)
-    out.append(run("cfg4 nmax2160 5min B=1", 2160, 1, None, "weights", lon=lon, lat=lat, lw=np.cos(lat * (np.pi / 180)), weight=w))
-    out.append(run("cfg4b nmax2160 5min B=16 (fused recursion kernels, no P table)", 2160, 16, None, "weights", lon=lon, lat=lat, lw=np.cos(lat * (np.pi / 180)), weight=w))
+    kw = dict(lon=lon, lat=lat, lw=np.cos(lat * (np.pi / 180)), weight=w)
+    add("cfg4 nmax2160 5min B=1", 2160, 1, None, "weights", **kw)
+    add("cfg4b nmax2160 5min B=16 (20 GB P table)", 2160, 16, None, "weights", **kw)
+    add("cfg4c nmax2160 5min B=16 (fused recursion kernels, no P table)", 2160, 16, None, "weights", flags=capi.FLAG_NO_PTABLE, **kw)
+    add("cfg4d nmax2160 5min B=64 (20 GB P table)", 2160, 64, None, "weights", **kw)
     json.dump(out, open("gpurun_out/configs_r01.json", "w"), indent=1)

@@ -7,7 +7,7 @@ top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 hdr = rows[1]
 idx = {h: i for i, h in enumerate(hdr)}
 stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
-data = rows[2:]
+data = [r for r in rows[2:] if len(r) >= len(hdr) and r[0] != hdr[0]]
 tot = sum(int(r[idx["# Samples"]] or 0) for r in data)
 print("total samples", tot)
 agg = {}
