@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_syn_fft(DevTables t, Params 
     const bool mirror = i2 >= 0;
     // ---- spectrum assembly: thread <-> (field f = tid % NF, orders m = tid / NF + i * NTHREADS / NF); fields fastest so
     // that a warp reads full 64/128-byte groups of G.  NF is a power of two.
-    const bool simple = 2 * N < K;                     // no aliasing: every slot is written at most once
+    const bool simple = 2 * N <= K;                    // no aliasing: every slot is written at most once (m = K/2 folds onto itself like m = 0)
     const int fsh = 31 - __clz(NF);
     const int f = tid & (NF - 1), mstep = NTHREADS >> fsh;
     double2* xf = smem2 + (size_t)f * fp.stride;
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_syn_fft(DevTables t, Params 
                     const double2 Wa = cmul(make_double2(A + Bp_, Ap - B), hp);
                     const double2 Wb = cmul(make_double2(A - Bp_, Ap + B), cconj(hp));
                     if (simple) {
-                        if (m0 + u * mstep == 0) xf[padi(pk[u])] = cadd(Wa, Wb);
+                        if (m0 + u * mstep == 0 || 2 * (m0 + u * mstep) == K) xf[padi(pk[u])] = cadd(Wa, Wb);
                         else { xf[padi(pk[u])] = Wa; xf[padi(pkc[u])] = Wb; }
                     } else if (sub == 0) {
                         double2* p = &xf[padi(pk[u])]; *p = cadd(*p, Wa);
@@ -371,7 +371,7 @@ static bool fft_params(int K, int Bp, fft::Params& fp) {
         if (c * per <= 220 * 1024) nf = c;
     if (nf == 0) return false;
     fp.NF = nf;
-    fp.TPT = nf >= 4 ? 64 : (nf == 2 ? 128 : 256);
+    fp.TPT = fft::MAXTHREADS / nf;                 // always a full 512-thread CTA: long transforms get more threads each
     fp.nthreads = fp.NF * fp.TPT;
     return true;
 }

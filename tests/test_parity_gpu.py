@@ -317,7 +317,9 @@ def test_aliased_longitudes_and_odd_rows(engine, flags):
     c = S.random_coefficients(nmax, B, kaula=False, seed=9)
     for lon, lat in ((np.arange(48) * 7.5, np.arange(-90.0, 90.1, 10.0)),            # K=48 < 81, equator + poles
                      (np.arange(-180.0, 180.0, 12.0), np.arange(-85.0, 86.0, 17.0)),  # K=30 = 2*3*5, lon0 = -180
-                     (np.arange(20) * 18.0 + 3.0, np.array([-30.0, 12.5, 30.0]))):    # K=20, offset start, one mirror pair + a single
+                     (np.arange(20) * 18.0 + 3.0, np.array([-30.0, 12.5, 30.0])),     # K=20, offset start, one mirror pair + a single
+                     (np.arange(80) * 4.5, np.arange(-88.0, 89.0, 4.0)),              # K=80 = 2*nmax: order nmax sits on the Nyquist slot (5' grid at nmax 2160)
+                     (np.arange(81) * (360.0 / 81), np.arange(-88.0, 89.0, 8.0))):    # K=81 = 2*nmax+1: first alias-free length
         ref = np.moveaxis(O.synthesis(c, n, m, lon, lat, kind="port"), 2, 0)
         out = engine.synthesis(c, n, m, lon, lat, flags=flags)
         assert per_field_err(out, ref) <= TOL
@@ -325,6 +327,12 @@ def test_aliased_longitudes_and_odd_rows(engine, flags):
     lon = np.arange(0.0, 360.0, 12.0)
     lat = np.arange(-87.0, 88.0, 6.0)
     f = np.random.default_rng(4).standard_normal((B, len(lat), len(lon)))
+    ref = O.analysis(f, nmax, lon, lat, kind="port")
+    out = engine.analysis(f, nmax, lon, lat, quadrature="shlib", flags=flags)
+    assert per_field_err(out, ref) <= TOL
+    # K = 2*nmax
+    lon = np.arange(0.0, 360.0, 4.5)
+    f = np.random.default_rng(5).standard_normal((B, len(lat), len(lon)))
     ref = O.analysis(f, nmax, lon, lat, kind="port")
     out = engine.analysis(f, nmax, lon, lat, quadrature="shlib", flags=flags)
     assert per_field_err(out, ref) <= TOL
