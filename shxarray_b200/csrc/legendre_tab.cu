@@ -52,27 +52,32 @@ void launch_ptab_gen(const Plan& p, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------
-namespace ts {
-constexpr int TR = 64, CH = 16, NCOLS = 128;
-constexpr int CROW = NCOLS + 2;
-constexpr int STAGES = 8;
-constexpr int NCONS = 256, NTHREADS = NCONS + 32;
-struct __align__(16) Stage {
-    double P[2 * PT_SUB];        // two 32-row sub-tiles [16][34]
-    double C[CH * CROW];         // [16][crow], crow = Cs (single column tile, one bulk copy) or 130 (row copies)
+// Tile shapes: the 8 consumer warps form NWR x NWC blocks of 32 rows x 32 columns.  NWC = 4 (128 columns, 64 rows) for
+// plans with more than 64 columns; NWC = 2 / 1 (64 / 32 columns, 128 / 256 rows) for narrower plans, so that 16 or 32
+// fields do not pay for 128 columns (r01: 16 fields at nmax 2160 cost the same 18.5 ms as 64).
+template <int NWC>
+struct TS {
+    static constexpr int NWR = 8 / NWC, TR = 32 * NWR, CH = 16, NCOLS = 32 * NWC;
+    static constexpr int CROW = NCOLS + 2;
+    static constexpr int PSZ = NWR * PT_SUB;          // NWR consecutive 32-row sub-tiles [16][34] of the table: one bulk copy
+    static constexpr int CSZ = CH * CROW;             // [16][crow], crow = Cs (single column tile, one bulk copy) or NCOLS + 2 (row copies)
+    static constexpr int STAGE = PSZ + CSZ;           // doubles
+    static constexpr int STAGES = NWC == 1 ? 5 : 8;
+    static constexpr int NCONS = 256, NTHREADS = NCONS + 32;
+    static constexpr size_t SMEM = sizeof(double) * STAGE * STAGES + 2 * STAGES * sizeof(uint64_t);
 };
-constexpr size_t SMEM = sizeof(Stage) * STAGES + 2 * STAGES * sizeof(uint64_t);
-}  // namespace ts
 
 // Persistent: gridDim.x CTAs (one per SM) walk the (order, row-tile) list in snake order -- tile k*P + c on even
 // rounds, k*P + P-1-c on odd rounds; orders ascend, so work descends and every CTA gets the same total -- and the TMA
 // warp keeps filling the ring across tile boundaries, so the tensor pipe does not drain 29 times per SM per launch.
-__global__ void __launch_bounds__(ts::NTHREADS, 1) k_leg_syn_tab(DevTables t, const double* __restrict__ Ptab, const double* __restrict__ Cm,
-                                                                  double* __restrict__ G, int nrt, int ntiles) {
-    using namespace ts;
+template <int NWC>
+__global__ void __launch_bounds__(TS<NWC>::NTHREADS, 1) k_leg_syn_tab(DevTables t, const double* __restrict__ Ptab, const double* __restrict__ Cm,
+                                                                       double* __restrict__ G, int nrt, int ntiles) {
+    using C_ = TS<NWC>;
+    constexpr int NWR = C_::NWR, TR = C_::TR, CH = C_::CH, NCOLS = C_::NCOLS, CROW = C_::CROW, STAGES = C_::STAGES, NCONS = C_::NCONS, NTHREADS = C_::NTHREADS;
     extern __shared__ __align__(128) unsigned char smraw[];
-    Stage* st = reinterpret_cast<Stage*>(smraw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smraw + sizeof(Stage) * STAGES);
+    double* stg = reinterpret_cast<double*>(smraw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smraw + sizeof(double) * C_::STAGE * STAGES);
     uint64_t* empty = full + STAGES;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int col0 = blockIdx.y * NCOLS;
@@ -88,7 +93,7 @@ __global__ void __launch_bounds__(ts::NTHREADS, 1) k_leg_syn_tab(DevTables t, co
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (!onecopy) {      // pad columns / rows of a partial column tile are never written by the row copies
-        for (int i = tid; i < (int)(sizeof(Stage) * STAGES / 8); i += NTHREADS) reinterpret_cast<double*>(smraw)[i] = 0.0;
+        for (int i = tid; i < C_::STAGE * STAGES; i += NTHREADS) stg[i] = 0.0;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
@@ -102,31 +107,34 @@ __global__ void __launch_bounds__(ts::NTHREADS, 1) k_leg_syn_tab(DevTables t, co
             const int m = tile / nrt, rt = tile - m * nrt;
             const int nchunks = (N - m + CH) / CH;
             const int64_t tmm = tri(m, m, N);
-            const double* psrc = Ptab + (t.pt_base[m] * t.RT32 + 2 * rt) * PT_SUB;
+            // sub-tiles past the last row tile of the order belong to the next degree block (or the slack behind the
+            // table): fetched with the rest, never used
+            const double* psrc = Ptab + (t.pt_base[m] * t.RT32 + NWR * rt) * PT_SUB;
             for (int ch = 0; ch < nchunks; ++ch, ++gc) {
                 const int s = gc % STAGES;
                 mbar_wait(&empty[s], ((gc / STAGES) & 1) ^ 1);
                 const int k0 = ch * CH;
+                double* sp = stg + s * C_::STAGE;
                 if (onecopy) {
                     if (lane == 0) {
-                        mbar_arrive_expect_tx(&full[s], (uint32_t)((2 * PT_SUB + CH * crow) * 8));
-                        bulk_g2s(&st[s].P[0], psrc + (int64_t)ch * t.RT32 * PT_SUB, 2 * PT_SUB * 8, &full[s]);
-                        bulk_g2s(&st[s].C[0], Cm + (tmm + k0) * t.Cs, (uint32_t)(CH * crow * 8), &full[s]);
+                        mbar_arrive_expect_tx(&full[s], (uint32_t)((C_::PSZ + CH * crow) * 8));
+                        bulk_g2s(sp, psrc + (int64_t)ch * t.RT32 * PT_SUB, C_::PSZ * 8, &full[s]);
+                        bulk_g2s(sp + C_::PSZ, Cm + (tmm + k0) * t.Cs, (uint32_t)(CH * crow * 8), &full[s]);
                     }
                 } else {
                     const int valid = min(CH, N - m - k0 + 1);
                     if (lane == 0) {
-                        mbar_arrive_expect_tx(&full[s], (uint32_t)(2 * PT_SUB * 8 + valid * ncols * 8));
-                        bulk_g2s(&st[s].P[0], psrc + (int64_t)ch * t.RT32 * PT_SUB, 2 * PT_SUB * 8, &full[s]);
+                        mbar_arrive_expect_tx(&full[s], (uint32_t)(C_::PSZ * 8 + valid * ncols * 8));
+                        bulk_g2s(sp, psrc + (int64_t)ch * t.RT32 * PT_SUB, C_::PSZ * 8, &full[s]);
                         for (int j = 0; j < valid; ++j)
-                            bulk_g2s(&st[s].C[j * crow], Cm + (tmm + k0 + j) * t.Cs + col0, (uint32_t)(ncols * 8), &full[s]);
+                            bulk_g2s(sp + C_::PSZ + j * crow, Cm + (tmm + k0 + j) * t.Cs + col0, (uint32_t)(ncols * 8), &full[s]);
                     }
                 }
             }
         }
     } else {
         // ------------------------------------------------------------------ consumers
-        const int wr = warp >> 2, wc = warp & 3;
+        const int wr = warp / NWC, wc = warp % NWC;
         const int lr = lane >> 2, lk = lane & 3;
         int gc = 0;
         int prev = -1;      // stage whose fragments were consumed last; released only after the NEXT stage has been acquired
@@ -136,6 +144,7 @@ __global__ void __launch_bounds__(ts::NTHREADS, 1) k_leg_syn_tab(DevTables t, co
             const int m = tile / nrt, rt = tile - m * nrt;
             const int nchunks = (N - m + CH) / CH;
             const int row0 = rt * TR;
+            const bool wlive = row0 + 32 * wr < R;      // this warp's 32 rows exist (last row tile of a tall tile shape)
             double acc[2][4][4][2];
 #pragma unroll
             for (int e = 0; e < 2; ++e)
@@ -152,8 +161,9 @@ __global__ void __launch_bounds__(ts::NTHREADS, 1) k_leg_syn_tab(DevTables t, co
                 // has been consumed by DMMAs issued in the previous loop iteration.
                 if (prev >= 0) { __syncwarp(); if (lane == 0) mbar_arrive(&empty[prev]); }
                 prev = s;
-                const double* __restrict__ SP = st[s].P + wr * PT_SUB + lr;
-                const double* __restrict__ SC = st[s].C + 32 * wc + lr;
+                if (NWC < 4 && !wlive) continue;
+                const double* __restrict__ SP = stg + s * C_::STAGE + wr * PT_SUB + lr;
+                const double* __restrict__ SC = stg + s * C_::STAGE + C_::PSZ + 32 * wc + lr;
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
@@ -187,23 +197,31 @@ __global__ void __launch_bounds__(ts::NTHREADS, 1) k_leg_syn_tab(DevTables t, co
 }
 
 // ------------------------------------------------------------------------------------------------
-namespace ta {
-constexpr int RT = 32, NS = 32, SB = 128, NCOLS = 128;
-constexpr int CROW = NCOLS + 2;
-constexpr int PSTAGES = 8;
-constexpr int NCONS = 256, NTHREADS = NCONS + 32;
-struct __align__(16) GTile { double g[RT * 2 * CROW]; };     // [32 rows][E/O][grow]
-struct __align__(16) PTile { double p[2 * PT_SUB]; };        // two 16-degree sub-tiles [16][34]
-constexpr size_t SMEM = sizeof(GTile) * 2 + sizeof(PTile) * PSTAGES + sizeof(uint64_t) * (2 * PSTAGES + 4);
-}  // namespace ta
+// Analysis.  The 8 consumer warps are (parity e) x (NCQ column quarters of 32) x (NDG = 4 / NCQ degree groups); each holds
+// 64 degrees of its parity x 32 columns of sums in registers.  NCQ = 4: CTA = (m, 128 columns), 128-degree super-blocks;
+// NCQ = 2 / 1 for plans of <= 64 / 32 columns: the spare warps take further degrees instead of idle columns, so a
+// super-block (= one pass over all latitude rows of G) spans 256 / 512 degrees and a stage 64 / 128.
+template <int NCQ>
+struct TA {
+    static constexpr int NDG = 4 / NCQ;
+    static constexpr int RT = 32, NS = 32 * NDG, SB = 4 * NS, NCOLS = 32 * NCQ;
+    static constexpr int CROW = NCOLS + 2;
+    static constexpr int PSTAGES = NCQ == 1 ? 5 : 8;
+    static constexpr int NCONS = 256, NTHREADS = NCONS + 32;
+    static constexpr int GSZ = RT * 2 * CROW;         // [32 rows][E/O][grow] doubles
+    static constexpr int PSZ = 2 * NDG * PT_SUB;      // 2 NDG 16-degree sub-tiles [16][34]
+    static constexpr size_t SMEM = sizeof(double) * (2 * GSZ + PSTAGES * PSZ) + sizeof(uint64_t) * (2 * PSTAGES + 4);
+};
 
-__global__ void __launch_bounds__(ta::NTHREADS, 1) k_leg_ana_tab(DevTables t, const double* __restrict__ Ptab, const double* __restrict__ G,
-                                                                  double* __restrict__ Cm) {
-    using namespace ta;
+template <int NCQ>
+__global__ void __launch_bounds__(TA<NCQ>::NTHREADS, 1) k_leg_ana_tab(DevTables t, const double* __restrict__ Ptab, const double* __restrict__ G,
+                                                                       double* __restrict__ Cm) {
+    using C_ = TA<NCQ>;
+    constexpr int NDG = C_::NDG, RT = C_::RT, NS = C_::NS, SB = C_::SB, NCOLS = C_::NCOLS, PSTAGES = C_::PSTAGES, NCONS = C_::NCONS;
     extern __shared__ __align__(128) unsigned char smraw[];
-    GTile* gt = reinterpret_cast<GTile*>(smraw);
-    PTile* ptile = reinterpret_cast<PTile*>(smraw + sizeof(GTile) * 2);
-    uint64_t* pfull = reinterpret_cast<uint64_t*>(smraw + sizeof(GTile) * 2 + sizeof(PTile) * PSTAGES);
+    double* gt = reinterpret_cast<double*>(smraw);                  // [2][GSZ]
+    double* ptile = gt + 2 * C_::GSZ;                               // [PSTAGES][PSZ]
+    uint64_t* pfull = reinterpret_cast<uint64_t*>(ptile + PSTAGES * C_::PSZ);
     uint64_t* pempty = pfull + PSTAGES;
     uint64_t* gfull = pempty + PSTAGES;
     uint64_t* gempty = gfull + 2;
@@ -214,7 +232,7 @@ __global__ void __launch_bounds__(ta::NTHREADS, 1) k_leg_ana_tab(DevTables t, co
     const int nsb = (N - m + SB) / SB;
     const int nrt = (R + RT - 1) / RT;
     const int64_t tmm = tri(m, m, N);
-    constexpr int grow = CROW;
+    constexpr int grow = C_::CROW;
 
     if (tid == 0) {
         for (int s = 0; s < PSTAGES; ++s) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], NCONS / 32); }
@@ -239,26 +257,26 @@ __global__ void __launch_bounds__(ta::NTHREADS, 1) k_leg_ana_tab(DevTables t, co
                     __syncwarp();
                     if (lane < nr) {
                         const double* src = G + (((int64_t)m * R + rt * RT + lane) * 2) * t.Gs + col0;
-                        bulk_g2s(&gt[gb].g[(lane * 2 + 0) * grow], src, (uint32_t)(ncols * 8), &gfull[gb]);
-                        bulk_g2s(&gt[gb].g[(lane * 2 + 1) * grow], src + t.Gs, (uint32_t)(ncols * 8), &gfull[gb]);
+                        bulk_g2s(&gt[gb * C_::GSZ + (lane * 2 + 0) * grow], src, (uint32_t)(ncols * 8), &gfull[gb]);
+                        bulk_g2s(&gt[gb * C_::GSZ + (lane * 2 + 1) * grow], src + t.Gs, (uint32_t)(ncols * 8), &gfull[gb]);
                     }
                 }
                 for (int inner = 0; inner < ninner; ++inner, ++sidx) {
                     const int s = sidx % PSTAGES;
                     mbar_wait(&pempty[s], ((sidx / PSTAGES) & 1) ^ 1);
                     const int k0 = sb * SB + inner * NS;
-                    const int nblk = (N - m - k0 + 1) > 16 ? 2 : 1;                 // 16-degree blocks of this stage that exist
+                    const int nblk = min(2 * NDG, (N - m - k0 + 16) / 16);          // 16-degree blocks of this stage that exist
                     if (lane == 0) {
                         mbar_arrive_expect_tx(&pfull[s], (uint32_t)(nblk * PT_SUB * 8));
                         for (int q = 0; q < nblk; ++q)
-                            bulk_g2s(&ptile[s].p[q * PT_SUB], pbase + ((int64_t)(k0 / 16 + q) * t.RT32 + rt) * PT_SUB, PT_SUB * 8, &pfull[s]);
+                            bulk_g2s(&ptile[s * C_::PSZ + q * PT_SUB], pbase + ((int64_t)(k0 / 16 + q) * t.RT32 + rt) * PT_SUB, PT_SUB * 8, &pfull[s]);
                     }
                 }
             }
         }
     } else {
         // ------------------------------------------------------------------ consumers
-        const int e = warp & 1, cq = warp >> 1;
+        const int e = warp & 1, cq = (warp >> 1) % NCQ, dg = (warp >> 1) / NCQ;
         const int lr = lane >> 2, lk = lane & 3;
         double acc[8][4][2];
         int sidx = 0;
@@ -276,7 +294,7 @@ __global__ void __launch_bounds__(ta::NTHREADS, 1) k_leg_ana_tab(DevTables t, co
                 mbar_wait(&gfull[gb], (it >> 1) & 1);
                 if (prev_g >= 0) { __syncwarp(); if (lane == 0) mbar_arrive(&gempty[prev_g]); }
                 prev_g = gb;
-                const double* __restrict__ GT = gt[gb].g + e * grow + 32 * cq + lr;
+                const double* __restrict__ GT = gt + gb * C_::GSZ + e * grow + 32 * cq + lr;
 #pragma unroll
                 for (int inner = 0; inner < SB / NS; ++inner) {
                     if (inner >= ninner) break;
@@ -285,8 +303,11 @@ __global__ void __launch_bounds__(ta::NTHREADS, 1) k_leg_ana_tab(DevTables t, co
                     ++sidx;
                     if (prev_s >= 0) { __syncwarp(); if (lane == 0) mbar_arrive(&pempty[prev_s]); }
                     prev_s = s;
-                    const double* __restrict__ PT = ptile[s].p + (2 * lr + e) * 34 + lk;
-                    const bool two = (N - m - (sb * SB + inner * NS) + 1) > 16;     // second 16-degree block present
+                    // degrees of this warp in the stage: two 16-degree blocks starting at kw
+                    const int kw = sb * SB + inner * NS + 32 * dg;
+                    if (NDG > 1 && kw > N - m) continue;                            // both blocks past nmax: nothing was copied
+                    const double* __restrict__ PT = ptile + s * C_::PSZ + 2 * dg * PT_SUB + (2 * lr + e) * 34 + lk;
+                    const bool two = (N - m - kw + 1) > 16;                         // second 16-degree block present
                     auto kstep = [&](int ks, bool rowok) {
                         double A[2], B[4];
                         A[0] = PT[4 * ks];
@@ -314,7 +335,7 @@ __global__ void __launch_bounds__(ta::NTHREADS, 1) k_leg_ana_tab(DevTables t, co
             }
 #pragma unroll
             for (int nb = 0; nb < 8; ++nb) {
-                const int k = sb * SB + 16 * nb + 2 * lr + e;
+                const int k = sb * SB + (nb >> 1) * NS + 32 * dg + 16 * (nb & 1) + 2 * lr + e;
                 if (k > N - m) continue;
 #pragma unroll
                 for (int cb = 0; cb < 4; ++cb) {
@@ -326,32 +347,48 @@ __global__ void __launch_bounds__(ta::NTHREADS, 1) k_leg_ana_tab(DevTables t, co
     }
 }
 
-bool launch_legendre_syn_tab(const Plan& p, cudaStream_t st) {
-    if (!p.Ptab || p.NC < 32) return false;
+template <int NWC>
+static bool launch_syn_tab_nwc(const Plan& p, cudaStream_t st) {
+    using C_ = TS<NWC>;
     static bool attr = false;
     if (!attr) {
-        if (cudaFuncSetAttribute(k_leg_syn_tab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts::SMEM) != cudaSuccess) return false;
+        if (cudaFuncSetAttribute(k_leg_syn_tab<NWC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_::SMEM) != cudaSuccess) return false;
         attr = true;
     }
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-    const int nrt = (p.nrows + ts::TR - 1) / ts::TR, ntiles = nrt * (p.nmax + 1);
-    const int ncolt = (p.NC + ts::NCOLS - 1) / ts::NCOLS;
+    const int nrt = (p.nrows + C_::TR - 1) / C_::TR, ntiles = nrt * (p.nmax + 1);
+    const int ncolt = (p.NC + C_::NCOLS - 1) / C_::NCOLS;
     dim3 grid(std::max(1, std::min(ntiles, sms / std::min(ncolt, sms))), ncolt);
-    k_leg_syn_tab<<<grid, ts::NTHREADS, ts::SMEM, st>>>(p.t, p.Ptab, p.Cm, p.G, nrt, ntiles);
+    k_leg_syn_tab<NWC><<<grid, C_::NTHREADS, C_::SMEM, st>>>(p.t, p.Ptab, p.Cm, p.G, nrt, ntiles);
+    return true;
+}
+
+bool launch_legendre_syn_tab(const Plan& p, cudaStream_t st) {
+    if (!p.Ptab || p.NC < 32) return false;
+    if (p.NC <= 32) return launch_syn_tab_nwc<1>(p, st);
+    if (p.NC <= 64) return launch_syn_tab_nwc<2>(p, st);
+    return launch_syn_tab_nwc<4>(p, st);
+}
+
+template <int NCQ>
+static bool launch_ana_tab_ncq(const Plan& p, cudaStream_t st) {
+    using C_ = TA<NCQ>;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(k_leg_ana_tab<NCQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_::SMEM) != cudaSuccess) return false;
+        attr = true;
+    }
+    dim3 grid(ana_order_count(p), (p.NC + C_::NCOLS - 1) / C_::NCOLS);
+    k_leg_ana_tab<NCQ><<<grid, C_::NTHREADS, C_::SMEM, st>>>(p.t, p.Ptab, p.G, p.Cm);
     return true;
 }
 
 bool launch_legendre_ana_tab(const Plan& p, cudaStream_t st) {
     if (!p.Ptab || p.NC < 32) return false;
-    static bool attr = false;
-    if (!attr) {
-        if (cudaFuncSetAttribute(k_leg_ana_tab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ta::SMEM) != cudaSuccess) return false;
-        attr = true;
-    }
-    dim3 grid(ana_order_count(p), (p.NC + ta::NCOLS - 1) / ta::NCOLS);
-    k_leg_ana_tab<<<grid, ta::NTHREADS, ta::SMEM, st>>>(p.t, p.Ptab, p.G, p.Cm);
-    return true;
+    if (p.NC <= 32) return launch_ana_tab_ncq<1>(p, st);
+    if (p.NC <= 64) return launch_ana_tab_ncq<2>(p, st);
+    return launch_ana_tab_ncq<4>(p, st);
 }
 
 }  // namespace shb

@@ -277,7 +277,8 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
         // tiled layout: [order][16-degree block][32-row tile][16][34] doubles (legendre_tab.cu)
         std::vector<int64_t> ptb(N + 2, 0);
         for (int m = 0; m <= N; ++m) ptb[m + 1] = ptb[m] + (N - m + 16) / 16;
-        const size_t pt_elems = (size_t)ptb[N + 1] * (p.Rpad / 32) * (16 * 34);
+        // + 8 sub-tiles of slack: the tall tile shapes of the narrow-column kernels fetch up to 8 sub-tiles at once, also at the very end
+        const size_t pt_elems = (size_t)ptb[N + 1] * (p.Rpad / 32) * (16 * 34) + 8 * (16 * 34);
         // default budget: a quarter of the device's memory (45 GiB on a 180 GB B200), and never more than what is free now
         // less 4 GiB of headroom.  At nmax 2160 x 1080 row pairs the table is 20 GB; streaming it (2.9 ms at HBM speed) beats
         // recomputing P_nm per call (the fused kernels) by 6-10 x for multi-field batches.

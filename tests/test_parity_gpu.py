@@ -252,11 +252,14 @@ def test_edge_cases(engine):
 
 
 @pytest.mark.parametrize("nmax,B,gtype,extra", [(720, 64, "gauss", 0), (96, 240, "regular", 0), (2160, 16, "regular_lon0", 0),
-                                                (360, 40, "regular", capi.FLAG_NO_PTABLE), (96, 100, "regular_lon0", capi.FLAG_NO_PTABLE)])
+                                                (360, 40, "regular", capi.FLAG_NO_PTABLE), (96, 100, "regular_lon0", capi.FLAG_NO_PTABLE),
+                                                (2160, 16, "regular_lon0", capi.FLAG_NO_PTABLE),
+                                                # narrow-column tile shapes of the table kernels: 32 columns (12 fields), 48 of 64 (24), 64 (32), 80 of 128 (40)
+                                                (600, 12, "gauss", 0), (300, 24, "gauss", 0), (300, 32, "regular", 0), (200, 40, "gauss", 0)])
 def test_dmma_kernels_match_bitfaithful_dfma_kernels(engine, nmax, B, gtype, extra):
     """The DFMA kernels are bit-faithful to the reference's P_nm (test_device_recursion_bit_exact) and are oracle-checked
-    above.  At BASELINE batch sizes the tensor-core kernels -- P-table fed (extra=0) and with the fused on-the-fly
-    recursion (FLAG_NO_PTABLE, also what runs when the table exceeds its budget, e.g. nmax=2160) -- must agree with them
+    above.  At BASELINE batch sizes the tensor-core kernels -- P-table fed (extra=0; 20 GB of table at nmax=2160) and with
+    the fused on-the-fly recursion (FLAG_NO_PTABLE, also what runs when the table exceeds its budget) -- must agree with them
     to the parity tolerance, in both directions, for white (worst-case) and Kaula spectra."""
     import torch
     if gtype == "regular_lon0" and nmax == 2160:
@@ -402,7 +405,7 @@ def test_order_sharded_analysis_is_a_disjoint_partition(engine, nmax, B, flags):
     assert np.array_equal(again, full)
 
 
-@pytest.mark.parametrize("nmax,B,flags", [(96, 240, 0), (200, 64, 0), (200, 40, capi.FLAG_NO_PTABLE)])
+@pytest.mark.parametrize("nmax,B,flags", [(96, 240, 0), (200, 64, 0), (200, 40, capi.FLAG_NO_PTABLE), (600, 12, 0), (300, 24, 0), (300, 3, 0)])
 def test_repeated_transforms_are_deterministic(engine, nmax, B, flags):
     """Race detector for the warp-specialised kernels (mbarrier rings, TMA refills, persistent tile loop): 25 back-to-back
     transforms must give bit-identical results.  Two real races were caught this way in round 1 (a stage released while
