@@ -371,7 +371,10 @@ static bool fft_params(int K, int Bp, fft::Params& fp) {
         if (c * per <= 220 * 1024) nf = c;
     if (nf == 0) return false;
     fp.NF = nf;
-    fp.TPT = fft::MAXTHREADS / nf;                 // always a full 512-thread CTA: long transforms get more threads each
+    fp.TPT = fft::MAXTHREADS / nf;                 // a full 512-thread CTA: long transforms get more threads each
+    // short transforms: two 256-thread CTAs per SM (the 128-register kernels fill the register file with 512 threads) overlap
+    // one CTA's DRAM phases with the other's passes; one warp per transform
+    if (nf == 8 && 2 * (nf * per + 2048) <= 220 * 1024) fp.TPT = 32;
     fp.nthreads = fp.NF * fp.TPT;
     return true;
 }
