@@ -106,9 +106,18 @@ __device__ __forceinline__ void twiddle_powers(double2 w1, double2* w) {
 
 // one in-place pass over one transform (buffer x, skewed indexing).  DIT: twiddle inputs; DIF: twiddle outputs.
 // Butterflies are processed in chunks of UB with their twiddle loads (global, L2 latency) issued together up front.
-template <int R, bool DIT>
-__device__ __forceinline__ void pass(double2* __restrict__ x, int K, int Ns, int tpt, int lt, const double2* __restrict__ tw, double sgn) {
-    constexpr int UB = R >= 8 ? 3 : 4;
+// IO = 1: the last DIT pass (sub-transform length Ns*R = K) sends its outputs straight to the two grid rows (real part ->
+// primary latitude, imaginary part -> mirror) instead of back to shared memory; IO = 2: the first DIF pass takes its inputs
+// straight from the grid rows.  Element k + q*Ns of thread k: consecutive threads touch consecutive longitudes.
+struct RowIO {
+    double* o1; double* o2;            // rows of the primary / mirror latitude (o2 unused without a mirror)
+    int64_t gs_lon;
+    bool live, mirror;
+};
+template <int R, bool DIT, int IO>
+__device__ __forceinline__ void pass(double2* __restrict__ x, int K, int Ns, int tpt, int lt, const double2* __restrict__ tw, double sgn, const RowIO& io) {
+    // IO = 2 keeps the row values of the whole chunk in registers: at most 16 complex values per thread
+    constexpr int UB = IO == 2 ? (R >= 8 ? 2 : (R >= 4 ? 3 : 4)) : (R >= 8 ? 3 : 4);
     const int M = Ns * R, nb = K / R, tws = K / M;
     const bool pow2 = (Ns & (Ns - 1)) == 0;            // true for all passes before the first radix 3/5
     const int sh = 31 - __clz(Ns);
@@ -123,6 +132,22 @@ __device__ __forceinline__ void pass(double2* __restrict__ x, int K, int Ns, int
             kk[u] = k;
             w1[u] = (idx < nb && k > 0) ? tw[k * tws] : make_double2(1.0, 0.0);
         }
+        double2 vin[IO == 2 ? UB : 1][IO == 2 ? R : 1];
+        if (IO == 2) {
+            // all row loads of the chunk in flight before the first butterfly
+#pragma unroll
+            for (int u = 0; u < UB; ++u)
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    double2 v = make_double2(0.0, 0.0);
+                    if (base[u] >= 0 && io.live) {
+                        const int64_t j = (int64_t)(base[u] + q * Ns) * io.gs_lon;
+                        v.x = io.o1[j];
+                        if (io.mirror) v.y = io.o2[j];
+                    }
+                    vin[IO == 2 ? u : 0][IO == 2 ? q : 0] = v;
+                }
+        }
 #pragma unroll
         for (int u = 0; u < UB; ++u) {
             if (base[u] < 0) continue;
@@ -134,7 +159,7 @@ __device__ __forceinline__ void pass(double2* __restrict__ x, int K, int Ns, int
                 twiddle_powers<R>(ww, w);
             }
 #pragma unroll
-            for (int q = 0; q < R; ++q) v[q] = x[padi(base[u] + q * Ns)];
+            for (int q = 0; q < R; ++q) v[q] = IO == 2 ? vin[IO == 2 ? u : 0][IO == 2 ? q : 0] : x[padi(base[u] + q * Ns)];
             if (DIT && tw_on) {
 #pragma unroll
                 for (int q = 1; q < R; ++q) v[q] = cmul(v[q], w[q]);
@@ -144,19 +169,30 @@ __device__ __forceinline__ void pass(double2* __restrict__ x, int K, int Ns, int
 #pragma unroll
                 for (int q = 1; q < R; ++q) v[q] = cmul(v[q], w[q]);
             }
+            if (IO == 1) {
+                if (io.live) {
 #pragma unroll
-            for (int q = 0; q < R; ++q) x[padi(base[u] + q * Ns)] = v[q];
+                    for (int q = 0; q < R; ++q) {
+                        const int64_t j = (int64_t)(base[u] + q * Ns) * io.gs_lon;
+                        io.o1[j] = v[q].x;
+                        if (io.mirror) io.o2[j] = v[q].y;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < R; ++q) x[padi(base[u] + q * Ns)] = v[q];
+            }
         }
     }
 }
 
-template <bool DIT>
-__device__ __forceinline__ void run_pass(int R, double2* x, int K, int Ns, int tpt, int lt, const double2* tw, double sgn) {
-    if (R == 8) pass<8, DIT>(x, K, Ns, tpt, lt, tw, sgn);
-    else if (R == 4) pass<4, DIT>(x, K, Ns, tpt, lt, tw, sgn);
-    else if (R == 2) pass<2, DIT>(x, K, Ns, tpt, lt, tw, sgn);
-    else if (R == 3) pass<3, DIT>(x, K, Ns, tpt, lt, tw, sgn);
-    else pass<5, DIT>(x, K, Ns, tpt, lt, tw, sgn);
+template <bool DIT, int IO>
+__device__ __forceinline__ void run_pass(int R, double2* x, int K, int Ns, int tpt, int lt, const double2* tw, double sgn, const RowIO& io) {
+    if (R == 8) pass<8, DIT, IO>(x, K, Ns, tpt, lt, tw, sgn, io);
+    else if (R == 4) pass<4, DIT, IO>(x, K, Ns, tpt, lt, tw, sgn, io);
+    else if (R == 2) pass<2, DIT, IO>(x, K, Ns, tpt, lt, tw, sgn, io);
+    else if (R == 3) pass<3, DIT, IO>(x, K, Ns, tpt, lt, tw, sgn, io);
+    else pass<5, DIT, IO>(x, K, Ns, tpt, lt, tw, sgn, io);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -236,29 +272,17 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_syn_fft(DevTables t, Params 
     double2* x = smem2 + (size_t)tr * fp.stride;
     // the transforms of a CTA are independent from here on: per-transform named barriers let their passes and row
     // stores drift apart and overlap instead of marching in lock step
-    for (int s = 0; s < fp.nrad; ++s) {
-        run_pass<true>(fp.rad[s], x, K, fp.ns[s], fp.TPT, lt, t.tw, +1.0);
+    const int b = b0 + tr;
+    RowIO io;
+    io.live = b < batch; io.mirror = mirror; io.gs_lon = gs_lon;
+    io.o1 = grid + (int64_t)b * gs_b + (int64_t)i1 * gs_lat;
+    io.o2 = grid + (int64_t)b * gs_b + (int64_t)(mirror ? i2 : 0) * gs_lat;
+    for (int s = 0; s + 1 < fp.nrad; ++s) {
+        run_pass<true, 0>(fp.rad[s], x, K, fp.ns[s], fp.TPT, lt, t.tw, +1.0, io);
         group_sync(1 + tr, fp.TPT);
     }
-    // ---- store: real part -> primary latitude, imaginary part -> mirror latitude
-    const int b = b0 + tr;
-    if (b < batch) {
-        double* o1 = grid + (int64_t)b * gs_b + (int64_t)i1 * gs_lat;
-        double* o2 = grid + (int64_t)b * gs_b + (int64_t)(mirror ? i2 : 0) * gs_lat;
-        if (gs_lon == 1 && (K & 1) == 0 && ((reinterpret_cast<uintptr_t>(o1) | reinterpret_cast<uintptr_t>(o2)) & 15) == 0) {
-            for (int j = 2 * lt; j < K; j += 2 * fp.TPT) {          // two longitudes per thread: 16-byte row stores
-                const double2 v0 = x[padi(j)], v1 = x[padi(j + 1)];
-                *reinterpret_cast<double2*>(o1 + j) = make_double2(v0.x, v1.x);
-                if (mirror) *reinterpret_cast<double2*>(o2 + j) = make_double2(v0.y, v1.y);
-            }
-        } else {
-            for (int j = lt; j < K; j += fp.TPT) {
-                const double2 v = x[padi(j)];
-                o1[(int64_t)j * gs_lon] = v.x;
-                if (mirror) o2[(int64_t)j * gs_lon] = v.y;
-            }
-        }
-    }
+    // ---- last pass + store: real part -> primary latitude, imaginary part -> mirror latitude
+    run_pass<true, 1>(fp.rad[fp.nrad - 1], x, K, fp.ns[fp.nrad - 1], fp.TPT, lt, t.tw, +1.0, io);
 }
 
 __global__ void __launch_bounds__(MAXTHREADS) k_lon_ana_fft(DevTables t, Params fp, const int* __restrict__ perm, int batch, const double* __restrict__ grid,
@@ -273,45 +297,19 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_ana_fft(DevTables t, Params 
     const int tr = tid / fp.TPT, lt = tid - tr * fp.TPT;
     double2* x = smem2 + (size_t)tr * fp.stride;
     {
+        // ---- first pass straight from the grid rows (primary latitude -> real part, mirror -> imaginary part); fields past
+        // the batch enter as zeros
         const int b = b0 + tr;
-        const bool live = b < batch;
-        const double* f1 = grid + (int64_t)b * gs_b + (int64_t)i1 * gs_lat;
-        const double* f2 = grid + (int64_t)b * gs_b + (int64_t)(mirror ? i2 : 0) * gs_lat;
-        if (live && gs_lon == 1 && (K & 1) == 0 && ((reinterpret_cast<uintptr_t>(f1) | reinterpret_cast<uintptr_t>(f2)) & 15) == 0) {
-            // two longitudes per thread per load (16-byte row loads), 6 iterations' loads in flight before the first use:
-            // this phase is pure DRAM latency (ncu r01: 38 % of the kernel's samples, all long-scoreboard)
-            constexpr int UL = 6;
-            for (int j0 = 2 * lt; j0 < K; j0 += 2 * fp.TPT * UL) {
-                double2 a[UL], c[UL];
-#pragma unroll
-                for (int u = 0; u < UL; ++u) {
-                    const int j = j0 + u * 2 * fp.TPT;
-                    if (j < K) {
-                        a[u] = *reinterpret_cast<const double2*>(f1 + j);
-                        c[u] = mirror ? *reinterpret_cast<const double2*>(f2 + j) : make_double2(0.0, 0.0);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < UL; ++u) {
-                    const int j = j0 + u * 2 * fp.TPT;
-                    if (j < K) {
-                        x[padi(j)] = make_double2(a[u].x, c[u].x);
-                        x[padi(j + 1)] = make_double2(a[u].y, c[u].y);
-                    }
-                }
-            }
-        } else {
-            for (int j = lt; j < K; j += fp.TPT) {
-                double2 v = make_double2(0.0, 0.0);
-                if (live) { v.x = f1[(int64_t)j * gs_lon]; if (mirror) v.y = f2[(int64_t)j * gs_lon]; }
-                x[padi(j)] = v;
-            }
+        RowIO io;
+        io.live = b < batch; io.mirror = mirror; io.gs_lon = gs_lon;
+        io.o1 = const_cast<double*>(grid) + (int64_t)b * gs_b + (int64_t)i1 * gs_lat;
+        io.o2 = const_cast<double*>(grid) + (int64_t)b * gs_b + (int64_t)(mirror ? i2 : 0) * gs_lat;
+        run_pass<false, 2>(fp.rad[fp.nrad - 1], x, K, fp.ns[fp.nrad - 1], fp.TPT, lt, t.tw, -1.0, io);
+        if (fp.nrad > 1) group_sync(1 + tr, fp.TPT);
+        for (int s = fp.nrad - 2; s >= 0; --s) {
+            run_pass<false, 0>(fp.rad[s], x, K, fp.ns[s], fp.TPT, lt, t.tw, -1.0, io);
+            if (s > 0) group_sync(1 + tr, fp.TPT);
         }
-    }
-    group_sync(1 + tr, fp.TPT);
-    for (int s = fp.nrad - 1; s >= 0; --s) {
-        run_pass<false>(fp.rad[s], x, K, fp.ns[s], fp.TPT, lt, t.tw, -1.0);
-        if (s > 0) group_sync(1 + tr, fp.TPT);
     }
     __syncthreads();
     {
