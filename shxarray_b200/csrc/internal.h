@@ -102,6 +102,9 @@ struct Plan {
     double* stage_coef = nullptr; int64_t stage_coef_elems = 0;
     double* stage_grid = nullptr; int64_t stage_grid_elems = 0;
     cudaStream_t own_stream = nullptr;
+    // host entry points: copy-in / copy-out streams and per-chunk events of the chunked duplex pipeline (plan.cu)
+    cudaStream_t in_stream = nullptr, out_stream = nullptr;
+    cudaEvent_t ev_in[8] = {}, ev_cmp[8] = {};
     int launches_syn = 0, launches_ana = 0;
     cudaEvent_t ev[8] = {};     // SHB200_FLAG_TIMING: syn 0..3, ana 4..7
     bool timed_syn = false, timed_ana = false;

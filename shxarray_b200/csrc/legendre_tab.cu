@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(TS<NWC>::NTHREADS, 1) k_leg_syn_tab(DevTables 
     const int col0 = blockIdx.y * NCOLS;
     const int N = t.nmax, R = t.nrows, NC = t.NC;
     const int ncols = min(NCOLS, NC - col0);
-    const bool onecopy = NC <= NCOLS;                  // whole rows of Cm fit the tile: contiguous block, padded stride Cs
+    const bool onecopy = t.Cs <= CROW;                 // whole (padded) rows of Cm fit the tile: one contiguous block, stride Cs
     const int crow = onecopy ? t.Cs : CROW;
     const int P = gridDim.x, c = blockIdx.x;
 

@@ -312,8 +312,26 @@ static void free_plan(Plan& p) {
     if (p.stage_coef) cudaFree(p.stage_coef);
     if (p.stage_grid) cudaFree(p.stage_grid);
     if (p.own_stream) cudaStreamDestroy(p.own_stream);
+    if (p.in_stream) cudaStreamDestroy(p.in_stream);
+    if (p.out_stream) cudaStreamDestroy(p.out_stream);
+    for (int i = 0; i < 8; ++i) { if (p.ev_in[i]) cudaEventDestroy(p.ev_in[i]); if (p.ev_cmp[i]) cudaEventDestroy(p.ev_cmp[i]); }
     for (int i = 0; i < 8; ++i) if (p.ev[i]) cudaEventDestroy(p.ev[i]);
 }
+
+// A call with fewer fields than the plan was made for runs on the leading columns only: fields come in groups of 8 with
+// their cosine and sine columns adjacent, so `batch` fields occupy the first 2*ceil8(batch) columns of every Cm / G row.
+// Row strides (Cs, Gs) stay those of the plan.  Restored when the launches have been issued (one stream at a time per plan).
+struct EffectiveWidth {
+    Plan& p;
+    int Bp0, NC0;
+    EffectiveWidth(Plan& plan, int batch) : p(plan), Bp0(plan.Bp), NC0(plan.NC) {
+        if (p.Bp > 8) {
+            const int bp = std::min(p.Bp, (batch + 7) / 8 * 8);
+            p.Bp = bp; p.NC = 2 * bp; p.t.Bp = bp; p.t.NC = 2 * bp;
+        }
+    }
+    ~EffectiveWidth() { p.Bp = Bp0; p.NC = NC0; p.t.Bp = Bp0; p.t.NC = NC0; }
+};
 
 static int check_batch(const Plan& p, int batch) {
     if (batch < 1 || batch > p.maxB) { set_error("batch must be in [1, max_batch] of the plan"); return SHB200_EINVAL; }
@@ -368,6 +386,7 @@ int shb200_synthesis(shb200_plan* plan, int32_t batch, const double* coef, int64
     SHB_CUDA(cudaSetDevice(p.device));
     cudaStream_t st = (cudaStream_t)stream;
     const bool tm = p.flags & SHB200_FLAG_TIMING;
+    EffectiveWidth width(p, batch);
     if (tm) cudaEventRecord(p.ev[0], st);
     launch_pack(p, batch, coef, cs_b, cs_nm, st);
     if (tm) cudaEventRecord(p.ev[1], st);
@@ -390,6 +409,7 @@ int shb200_analysis(shb200_plan* plan, int32_t batch, const double* grid, int64_
     SHB_CUDA(cudaSetDevice(p.device));
     cudaStream_t st = (cudaStream_t)stream;
     const bool tm = p.flags & SHB200_FLAG_TIMING;
+    EffectiveWidth width(p, batch);
     if (tm) cudaEventRecord(p.ev[4], st);
     rc = launch_lon_ana(p, batch, grid, gs_b, gs_lat, gs_lon, st);
     if (rc) return rc;
@@ -450,6 +470,25 @@ static int ensure_stage(double** buf, int64_t* have, int64_t need) {
     return 0;
 }
 
+// ---- host-buffer entry points ---------------------------------------------------------------------
+// The transforms are PCIe-bound here (cfg3: 0.27 + 0.57 GB per direction against ~3 ms of kernels), so the batch is cut into
+// up to 4 chunks of whole fields that flow through three streams: copy-in (H2D) -> kernels -> copy-out (D2H).  Both copy
+// directions then run at once (the link is full duplex) and the kernels hide behind them: time per call ~ the larger of the
+// two transfers instead of their sum plus the kernels.  Needs the batch axis to be the slowest of both host arrays (chunks
+// are then contiguous spans); anything else takes the single-shot path.
+static int host_chunks(int batch) { return batch >= 32 ? 4 : (batch >= 16 ? 2 : 1); }
+
+static int ensure_pipeline(Plan& p) {
+    if (p.in_stream) return 0;
+    SHB_CUDA(cudaStreamCreateWithFlags(&p.in_stream, cudaStreamNonBlocking));
+    SHB_CUDA(cudaStreamCreateWithFlags(&p.out_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; ++i) {
+        SHB_CUDA(cudaEventCreateWithFlags(&p.ev_in[i], cudaEventDisableTiming));
+        SHB_CUDA(cudaEventCreateWithFlags(&p.ev_cmp[i], cudaEventDisableTiming));
+    }
+    return 0;
+}
+
 int shb200_synthesis_host(shb200_plan* plan, int32_t batch, const double* coef, int64_t cs_b, int64_t cs_nm,
                           double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon) {
     if (!plan || !coef || !grid) { set_error("synthesis_host: null argument"); return SHB200_EINVAL; }
@@ -460,15 +499,39 @@ int shb200_synthesis_host(shb200_plan* plan, int32_t batch, const double* coef, 
     SHB_CUDA(cudaSetDevice(p.device));
     int64_t ncoef = span2(batch, cs_b, p.nsh, cs_nm);
     bool points = p.mode == SHB200_MODE_POINTS;
-    int64_t ngrid = points ? span2(batch, gs_b, p.nlat, gs_lat) : span2(batch, gs_b, p.nlat, gs_lat) + (p.nlon - 1) * gs_lon;
+    auto grid_span = [&](int64_t nb) { return points ? span2(nb, gs_b, p.nlat, gs_lat) : span2(nb, gs_b, p.nlat, gs_lat) + (p.nlon - 1) * gs_lon; };
+    int64_t ngrid = grid_span(batch);
     if ((rc = ensure_stage(&p.stage_coef, &p.stage_coef_elems, ncoef))) return rc;
     if ((rc = ensure_stage(&p.stage_grid, &p.stage_grid_elems, ngrid))) return rc;
-    SHB_CUDA(cudaMemcpyAsync(p.stage_coef, coef, sizeof(double) * ncoef, cudaMemcpyHostToDevice, p.own_stream));
-    rc = shb200_synthesis(plan, batch, p.stage_coef, cs_b, cs_nm, p.stage_grid, gs_b, gs_lat, gs_lon, p.own_stream);
-    if (rc) return rc;
-    SHB_CUDA(cudaMemcpyAsync(grid, p.stage_grid, sizeof(double) * ngrid, cudaMemcpyDeviceToHost, p.own_stream));
-    SHB_CUDA(cudaStreamSynchronize(p.own_stream));
-    return 0;
+    const int nchunk = host_chunks(batch);
+    const bool sliceable = cs_b >= span2(1, 0, p.nsh, cs_nm) && gs_b >= grid_span(1);
+    if (nchunk == 1 || !sliceable) {
+        SHB_CUDA(cudaMemcpyAsync(p.stage_coef, coef, sizeof(double) * ncoef, cudaMemcpyHostToDevice, p.own_stream));
+        rc = shb200_synthesis(plan, batch, p.stage_coef, cs_b, cs_nm, p.stage_grid, gs_b, gs_lat, gs_lon, p.own_stream);
+        if (rc) return rc;
+        SHB_CUDA(cudaMemcpyAsync(grid, p.stage_grid, sizeof(double) * ngrid, cudaMemcpyDeviceToHost, p.own_stream));
+        SHB_CUDA(cudaStreamSynchronize(p.own_stream));
+        return 0;
+    }
+    if ((rc = ensure_pipeline(p))) return rc;
+    const int per = ((batch + nchunk - 1) / nchunk + 7) / 8 * 8;         // whole groups of 8 fields per chunk
+    int c = 0;
+    for (int b0 = 0; b0 < batch; b0 += per, ++c) {
+        const int nb = std::min(per, batch - b0);
+        const int64_t co = (int64_t)b0 * cs_b, go = (int64_t)b0 * gs_b;
+        SHB_CUDA(cudaMemcpyAsync(p.stage_coef + co, coef + co, sizeof(double) * span2(nb, cs_b, p.nsh, cs_nm), cudaMemcpyHostToDevice, p.in_stream));
+        SHB_CUDA(cudaEventRecord(p.ev_in[c], p.in_stream));
+        SHB_CUDA(cudaStreamWaitEvent(p.own_stream, p.ev_in[c], 0));
+        rc = shb200_synthesis(plan, nb, p.stage_coef + co, cs_b, cs_nm, p.stage_grid + go, gs_b, gs_lat, gs_lon, p.own_stream);
+        if (rc) break;
+        SHB_CUDA(cudaEventRecord(p.ev_cmp[c], p.own_stream));
+        SHB_CUDA(cudaStreamWaitEvent(p.out_stream, p.ev_cmp[c], 0));
+        SHB_CUDA(cudaMemcpyAsync(grid + go, p.stage_grid + go, sizeof(double) * grid_span(nb), cudaMemcpyDeviceToHost, p.out_stream));
+    }
+    cudaStreamSynchronize(p.in_stream);
+    cudaStreamSynchronize(p.own_stream);
+    SHB_CUDA(cudaStreamSynchronize(p.out_stream));
+    return rc;
 }
 
 int shb200_analysis_host(shb200_plan* plan, int32_t batch, const double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon,
@@ -481,15 +544,39 @@ int shb200_analysis_host(shb200_plan* plan, int32_t batch, const double* grid, i
     SHB_CUDA(cudaSetDevice(p.device));
     int64_t nfull = (int64_t)(p.nmax + 1) * (p.nmax + 1);
     int64_t ncoef = span2(batch, cs_b, nfull, cs_nm);
-    int64_t ngrid = span2(batch, gs_b, p.nlat, gs_lat) + (p.nlon - 1) * gs_lon;
+    auto grid_span = [&](int64_t nb) { return span2(nb, gs_b, p.nlat, gs_lat) + (p.nlon - 1) * gs_lon; };
+    int64_t ngrid = grid_span(batch);
     if ((rc = ensure_stage(&p.stage_coef, &p.stage_coef_elems, ncoef))) return rc;
     if ((rc = ensure_stage(&p.stage_grid, &p.stage_grid_elems, ngrid))) return rc;
-    SHB_CUDA(cudaMemcpyAsync(p.stage_grid, grid, sizeof(double) * ngrid, cudaMemcpyHostToDevice, p.own_stream));
-    rc = shb200_analysis(plan, batch, p.stage_grid, gs_b, gs_lat, gs_lon, p.stage_coef, cs_b, cs_nm, p.own_stream);
-    if (rc) return rc;
-    SHB_CUDA(cudaMemcpyAsync(coef, p.stage_coef, sizeof(double) * ncoef, cudaMemcpyDeviceToHost, p.own_stream));
-    SHB_CUDA(cudaStreamSynchronize(p.own_stream));
-    return 0;
+    const int nchunk = host_chunks(batch);
+    const bool sliceable = cs_b >= span2(1, 0, nfull, cs_nm) && gs_b >= grid_span(1);
+    if (nchunk == 1 || !sliceable) {
+        SHB_CUDA(cudaMemcpyAsync(p.stage_grid, grid, sizeof(double) * ngrid, cudaMemcpyHostToDevice, p.own_stream));
+        rc = shb200_analysis(plan, batch, p.stage_grid, gs_b, gs_lat, gs_lon, p.stage_coef, cs_b, cs_nm, p.own_stream);
+        if (rc) return rc;
+        SHB_CUDA(cudaMemcpyAsync(coef, p.stage_coef, sizeof(double) * ncoef, cudaMemcpyDeviceToHost, p.own_stream));
+        SHB_CUDA(cudaStreamSynchronize(p.own_stream));
+        return 0;
+    }
+    if ((rc = ensure_pipeline(p))) return rc;
+    const int per = ((batch + nchunk - 1) / nchunk + 7) / 8 * 8;
+    int c = 0;
+    for (int b0 = 0; b0 < batch; b0 += per, ++c) {
+        const int nb = std::min(per, batch - b0);
+        const int64_t co = (int64_t)b0 * cs_b, go = (int64_t)b0 * gs_b;
+        SHB_CUDA(cudaMemcpyAsync(p.stage_grid + go, grid + go, sizeof(double) * grid_span(nb), cudaMemcpyHostToDevice, p.in_stream));
+        SHB_CUDA(cudaEventRecord(p.ev_in[c], p.in_stream));
+        SHB_CUDA(cudaStreamWaitEvent(p.own_stream, p.ev_in[c], 0));
+        rc = shb200_analysis(plan, nb, p.stage_grid + go, gs_b, gs_lat, gs_lon, p.stage_coef + co, cs_b, cs_nm, p.own_stream);
+        if (rc) break;
+        SHB_CUDA(cudaEventRecord(p.ev_cmp[c], p.own_stream));
+        SHB_CUDA(cudaStreamWaitEvent(p.out_stream, p.ev_cmp[c], 0));
+        SHB_CUDA(cudaMemcpyAsync(coef + co, p.stage_coef + co, sizeof(double) * span2(nb, cs_b, nfull, cs_nm), cudaMemcpyDeviceToHost, p.out_stream));
+    }
+    cudaStreamSynchronize(p.in_stream);
+    cudaStreamSynchronize(p.own_stream);
+    SHB_CUDA(cudaStreamSynchronize(p.out_stream));
+    return rc;
 }
 
 // Gauss-Legendre nodes/weights by Newton iteration on P_n in long double.

@@ -233,6 +233,54 @@ def test_device_tensor_path_matches_host_path(engine):
     assert np.array_equal(at.cpu().numpy(), ah)
 
 
+@pytest.mark.parametrize("nmax,B", [(96, 40), (200, 64), (60, 21)])
+def test_host_path_chunked_pipeline_matches_device_path(engine, nmax, B):
+    """Batches of >= 16 fields go through the host entry points in chunks on three streams (copy-in, kernels, copy-out);
+    the chunks run the narrower kernel shapes, so the comparison is to rounding, not bit for bit."""
+    import torch
+    grid = sb.lonlat_grid(nmax, gtype="gauss")
+    c = S.random_coefficients(nmax, B, kaula=False, seed=17)
+    fh = engine.synthesis(c, lon=grid["lon"], lat=grid["lat"], nmax=nmax)
+    ft = engine.synthesis(torch.from_numpy(c).cuda(), lon=grid["lon"], lat=grid["lat"], nmax=nmax).cpu().numpy()
+    assert per_field_err(fh, ft) <= 1e-13
+    ah = engine.analysis(fh, nmax, grid["lon"], grid["lat"], quadrature="gauss")
+    at = engine.analysis(torch.from_numpy(fh).cuda(), nmax, grid["lon"], grid["lat"], quadrature="gauss").cpu().numpy()
+    assert per_field_err(ah, at) <= 1e-13
+    assert per_field_err(ah, c) <= TOL
+    # nm-first (batch fastest) host arrays cannot be cut into contiguous chunks: single-shot path, same values
+    n, m = sb.nm_index(nmax)
+    fh2 = engine.synthesis(np.asfortranarray(c), n, m, grid["lon"], grid["lat"])
+    assert per_field_err(fh2, ft) <= 1e-13
+
+
+@pytest.mark.parametrize("flags", [0, capi.FLAG_NO_PTABLE])
+def test_plan_used_below_its_max_batch(flags):
+    """A plan made for 64 fields called with 3, 16 and 40 (the engine reuses a cached plan whose max_batch is large
+    enough): the kernels run on the leading 2*ceil8(batch) columns only -- narrow tile shapes, the DFMA / small-batch
+    kernels below 32 columns -- with the plan's row strides.  Compared with plans made for exactly that batch."""
+    import torch
+    nmax = 120
+    g = sb.lonlat_grid(nmax, gtype="gauss")
+    lat, lon = g["lat"], g["lon"]
+    big, exact = sb.SHEngine(0, flags=flags), sb.SHEngine(0, flags=flags)
+    c_all = torch.from_numpy(S.random_coefficients(nmax, 64, kaula=False, seed=23)).cuda()
+    f_all = big.synthesis(c_all, lon=lon, lat=lat, nmax=nmax)                    # creates and caches the 64-field plans
+    big.analysis(f_all, nmax, lon, lat, quadrature="gauss")
+    for B in (3, 16, 40):
+        c = c_all[:B].contiguous()
+        f = big.synthesis(c, lon=lon, lat=lat, nmax=nmax)
+        assert all(p.max_batch == 64 for p in big._plans.values())
+        f_ref = exact.synthesis(c, lon=lon, lat=lat, nmax=nmax)
+        num = (f - f_ref).abs().amax(dim=(1, 2)); den = f_ref.abs().amax(dim=(1, 2))
+        assert float((num / den).max()) <= 1e-13
+        a = big.analysis(f_ref, nmax, lon, lat, quadrature="gauss")
+        a_ref = exact.analysis(f_ref, nmax, lon, lat, quadrature="gauss")
+        num = (a - a_ref).abs().amax(dim=1); den = a_ref.abs().amax(dim=1)
+        assert float((num / den).max()) <= 1e-13
+        exact.clear()
+    big.clear()
+
+
 def test_edge_cases(engine):
     # nmax = 0, single latitude, single field; odd sizes; batch not a multiple of the column block
     out = engine.synthesis(np.array([[2.5]]), np.array([0]), np.array([0]), [10.0, 20.0, 30.0], [5.0])
@@ -449,7 +497,9 @@ def test_batch_chunking_and_strided_device_views(engine):
     assert np.array_equal(out_s.cpu().numpy(), ref)
     gt = torch.from_numpy(ref).cuda().permute(1, 2, 0).contiguous().permute(2, 0, 1)   # [B, lat, lon] view of [lat, lon, B] storage
     a_view = engine.analysis(gt, nmax, g["lon"], g["lat"])
-    assert np.array_equal(a_view.cpu().numpy(), engine.analysis(ref, nmax, g["lon"], g["lat"]))
+    assert np.array_equal(a_view.cpu().numpy(), engine.analysis(torch.from_numpy(ref).cuda(), nmax, g["lon"], g["lat"]).cpu().numpy())
+    # host arrays of >= 16 fields go through the chunked pipeline (7-field tail chunk: tiny-batch kernels): equal to rounding
+    assert per_field_err(a_view.cpu().numpy(), engine.analysis(ref, nmax, g["lon"], g["lat"])) <= 1e-13
 
 
 def test_c_abi_transform_from_plain_c(tmp_path):
