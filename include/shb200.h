@@ -108,7 +108,9 @@ int shb200_plan_set_order_shard(shb200_plan* plan, int32_t rank, int32_t world);
 /* Synthesis  f(b, point) = sum_k C(b,k) * Ybar_{n_k m_k}(point)      [synthesis.pyx:175-189]
  *   coef element (b,k)          at coef[b*cs_b + k*cs_nm]             (device pointer, element strides)
  *   grid element (b,ilat,ilon)  at grid[b*gs_b + ilat*gs_lat + ilon*gs_lon]; point mode: (b,i) at grid[b*gs_b + i*gs_lat]
- * Asynchronous on `stream` (a cudaStream_t); inputs are not modified. */
+ * Asynchronous on `stream` (a cudaStream_t); inputs are not modified.  1 <= batch <= max_batch; a call with fewer fields
+ * than the plan was made for works on the leading 2*ceil8(batch) columns of the plan's workspace only, so its cost follows
+ * `batch`, not `max_batch`.  A plan serves one stream at a time (its workspace is shared by consecutive calls). */
 int shb200_synthesis(shb200_plan* plan, int32_t batch, const double* coef, int64_t cs_b, int64_t cs_nm,
                      double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, void* stream);
 
@@ -118,7 +120,9 @@ int shb200_analysis(shb200_plan* plan, int32_t batch, const double* grid, int64_
                     double* coef, int64_t cs_b, int64_t cs_nm, void* stream);
 
 /* Same two calls on HOST buffers: host->device copy, transform, device->host copy, synchronous.
- * This is the call the reference-facing plugin makes for numpy-backed DataArrays. */
+ * This is the call the reference-facing plugin makes for numpy-backed DataArrays.  When the batch axis is the slowest
+ * axis of both arrays, batches of >= 16 fields are cut into up to 4 chunks that overlap copy-in, kernels and copy-out on
+ * three streams (pinned host memory is needed for the copies to be asynchronous; pageable memory works, without overlap). */
 int shb200_synthesis_host(shb200_plan* plan, int32_t batch, const double* coef, int64_t cs_b, int64_t cs_nm,
                           double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon);
 int shb200_analysis_host(shb200_plan* plan, int32_t batch, const double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon,
