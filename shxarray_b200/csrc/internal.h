@@ -61,6 +61,21 @@ struct Plan;
 
 // ---- kernels (launch wrappers; all asynchronous on `st`) --------------------------------------
 // pack: user coefficients -> Cm[tri][NC] ; unpack: Cm -> user (full triangle, position n^2+n+m)
+// cudaFuncSetAttribute applies to the current device only: launchers remember per device whether they have raised the
+// dynamic shared-memory limit of their kernel (one process may drive several GPUs through several plans).
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool first() {
+        int d = 0;
+        cudaGetDevice(&d);
+        if (d < 0 || d >= 64) return true;
+        const bool f = !done[d];
+        done[d] = true;
+        return f;
+    }
+};
+int device_sm_count();   // multiprocessors of the current device (cached per device)
+
 void launch_pack(const Plan& p, int batch, const double* coef, int64_t cs_b, int64_t cs_nm, cudaStream_t st);
 void launch_unpack(const Plan& p, int batch, double* coef, int64_t cs_b, int64_t cs_nm, cudaStream_t st);
 // Legendre stage

@@ -321,10 +321,9 @@ __global__ void __launch_bounds__(ana::NTHREADS, 1) k_leg_ana_dmma(DevTables t, 
 
 bool launch_legendre_syn_dmma(const Plan& p, cudaStream_t st) {
     if (p.NC < 32) return false;   // tiny batches: the one-row-per-thread DFMA kernel is the better shape
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.first()) {
         if (cudaFuncSetAttribute(dm::k_leg_syn_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm::SMEM_SYN) != cudaSuccess) return false;
-        attr = true;
     }
     dim3 grid((p.nrows + dm::TR - 1) / dm::TR, p.nmax + 1, (p.NC + dm::NCOLS - 1) / dm::NCOLS);
     dm::k_leg_syn_dmma<<<grid, dm::NTHREADS, dm::SMEM_SYN, st>>>(p.t, p.Cm, p.G);
@@ -335,10 +334,9 @@ bool launch_legendre_ana_dmma(const Plan& p, cudaStream_t st) {
     if (p.NC < 32 || p.nrows > ana::MAXROWS) return false;
     const int rows_padded = (p.nrows + ana::RT - 1) / ana::RT * ana::RT;
     const size_t smem = ana::smem_bytes(rows_padded);
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.first()) {
         if (cudaFuncSetAttribute(k_leg_ana_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ana::smem_bytes(ana::MAXROWS)) != cudaSuccess) return false;
-        attr = true;
     }
     dim3 grid(ana_order_count(p), (p.NC + ana::NCOLS - 1) / ana::NCOLS);
     k_leg_ana_dmma<<<grid, ana::NTHREADS, smem, st>>>(p.t, p.G, p.Cm, rows_padded);

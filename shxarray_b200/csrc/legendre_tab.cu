@@ -350,13 +350,11 @@ __global__ void __launch_bounds__(TA<NCQ>::NTHREADS, 1) k_leg_ana_tab(DevTables 
 template <int NWC>
 static bool launch_syn_tab_nwc(const Plan& p, cudaStream_t st) {
     using C_ = TS<NWC>;
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.first()) {
         if (cudaFuncSetAttribute(k_leg_syn_tab<NWC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_::SMEM) != cudaSuccess) return false;
-        attr = true;
     }
-    static int sms = 0;
-    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int sms = device_sm_count();
     const int nrt = (p.nrows + C_::TR - 1) / C_::TR, ntiles = nrt * (p.nmax + 1);
     const int ncolt = (p.NC + C_::NCOLS - 1) / C_::NCOLS;
     dim3 grid(std::max(1, std::min(ntiles, sms / std::min(ncolt, sms))), ncolt);
@@ -374,10 +372,9 @@ bool launch_legendre_syn_tab(const Plan& p, cudaStream_t st) {
 template <int NCQ>
 static bool launch_ana_tab_ncq(const Plan& p, cudaStream_t st) {
     using C_ = TA<NCQ>;
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.first()) {
         if (cudaFuncSetAttribute(k_leg_ana_tab<NCQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_::SMEM) != cudaSuccess) return false;
-        attr = true;
     }
     dim3 grid(ana_order_count(p), (p.NC + C_::NCOLS - 1) / C_::NCOLS);
     k_leg_ana_tab<NCQ><<<grid, C_::NTHREADS, C_::SMEM, st>>>(p.t, p.Ptab, p.G, p.Cm);

@@ -398,8 +398,8 @@ int launch_lon_syn_fft(const Plan& p, int batch, double* grid, int64_t gs_b, int
     fft::Params fp;
     fft_params(p.K, p.Bp, fp);
     size_t smem = (size_t)fp.NF * fp.stride * sizeof(double2);
-    static bool attr = false;
-    if (!attr) { SHB_CUDA(cudaFuncSetAttribute(fft::k_lon_syn_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+    static PerDeviceOnce attr;
+    if (attr.first()) { SHB_CUDA(cudaFuncSetAttribute(fft::k_lon_syn_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); }
     dim3 g((batch + fp.NF - 1) / fp.NF, p.nrows);
     fft::k_lon_syn_fft<<<g, fp.nthreads, smem, st>>>(p.t, fp, p.fft_perm, batch, p.G, grid, gs_b, gs_lat, gs_lon);
     return 0;
@@ -409,8 +409,8 @@ int launch_lon_ana_fft(const Plan& p, int batch, const double* grid, int64_t gs_
     fft::Params fp;
     fft_params(p.K, p.Bp, fp);
     size_t smem = (size_t)fp.NF * fp.stride * sizeof(double2);
-    static bool attr = false;
-    if (!attr) { SHB_CUDA(cudaFuncSetAttribute(fft::k_lon_ana_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+    static PerDeviceOnce attr;
+    if (attr.first()) { SHB_CUDA(cudaFuncSetAttribute(fft::k_lon_ana_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); }
     dim3 g((p.Bp + fp.NF - 1) / fp.NF, p.nrows);
     fft::k_lon_ana_fft<<<g, fp.nthreads, smem, st>>>(p.t, fp, p.fft_perm, batch, grid, gs_b, gs_lat, gs_lon, p.G);
     return 0;

@@ -502,6 +502,30 @@ def test_batch_chunking_and_strided_device_views(engine):
     assert per_field_err(a_view.cpu().numpy(), engine.analysis(ref, nmax, g["lon"], g["lat"])) <= 1e-13
 
 
+def test_two_devices_in_one_process():
+    """One process driving two GPUs through two engines (the per-device kernel attributes and plan caches must not be
+    shared): same results on both.  Skipped on single-GPU boxes."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    nmax, B = 200, 40
+    g = sb.lonlat_grid(nmax, gtype="gauss")
+    c = S.random_coefficients(nmax, B, kaula=False, seed=5)
+    outs = []
+    for dev in (0, 1):
+        eng = sb.SHEngine(device=dev)
+        ct = torch.from_numpy(c).to(f"cuda:{dev}")
+        f = eng.synthesis(ct, lon=g["lon"], lat=g["lat"], nmax=nmax)
+        a = eng.analysis(f, nmax, g["lon"], g["lat"], quadrature="gauss")
+        assert f.device.index == dev and a.device.index == dev
+        outs.append((f.cpu().numpy(), a.cpu().numpy()))
+        small = eng.synthesis(ct[:1], lon=g["lon"], lat=g["lat"], nmax=nmax, flags=capi.FLAG_NO_DMMA)   # DFMA kernels on this device too
+        assert per_field_err(small.cpu().numpy(), outs[-1][0][:1]) <= TOL
+        eng.clear()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert per_field_err(outs[0][1], c) <= TOL
+
+
 def test_c_abi_transform_from_plain_c(tmp_path):
     """The same C program as tests/test_host.py::test_c_abi_from_plain_c, on a GPU: plan_create + synthesis_host from C."""
     import shutil
