@@ -411,7 +411,9 @@ int launch_lon_ana_fft(const Plan& p, int batch, const double* grid, int64_t gs_
     size_t smem = (size_t)fp.NF * fp.stride * sizeof(double2);
     static PerDeviceOnce attr;
     if (attr.first()) { SHB_CUDA(cudaFuncSetAttribute(fft::k_lon_ana_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); }
-    dim3 g((p.Bp + fp.NF - 1) / fp.NF, p.nrows);
+    // field groups made of padding only are skipped: their G columns keep whatever they held (zeros after plan creation),
+    // and the Legendre stage's results for padded fields are never unpacked
+    dim3 g((batch + fp.NF - 1) / fp.NF, p.nrows);
     fft::k_lon_ana_fft<<<g, fp.nthreads, smem, st>>>(p.t, fp, p.fft_perm, batch, grid, gs_b, gs_lat, gs_lon, p.G);
     return 0;
 }
