@@ -27,6 +27,52 @@ struct Params {
     int rad[MAXRAD];   // DIT order (first pass has sub-transform length 1)
     int ns[MAXRAD];    // product of the previous radices
     unsigned magic[MAXRAD];   // ceil(2^32 / ns): idx / ns == __umulhi(idx, magic) for idx * ns < 2^32 (ns >= 2)
+    static constexpr bool is_static = false;
+    __host__ __device__ int K_() const { return K; }
+    __host__ __device__ int nrad_() const { return nrad; }
+    __host__ __device__ int NF_() const { return NF; }
+    __host__ __device__ int TPT_() const { return TPT; }
+    __host__ __device__ int stride_() const { return stride; }
+};
+
+// The same parameters as compile-time constants of K (for plans of >= 8 fields): the kernels below are instantiated for the
+// longitude counts of the usual grids (launch_lon_*_fft), which turns every stride, trip count and division of the
+// passes into immediates and drops the radices a length does not use (r01: -7 % / -11 % on the cfg3 longitude stages).
+template <int KK>
+struct Factors {
+    int n = 0;
+    int rad[MAXRAD] = {};
+    int ns[MAXRAD] = {};
+    unsigned magic[MAXRAD] = {};
+    constexpr Factors() {
+        int k = KK;
+        while (k % 8 == 0 && n < MAXRAD) { rad[n++] = 8; k /= 8; }
+        while (k % 4 == 0 && n < MAXRAD) { rad[n++] = 4; k /= 4; }
+        while (k % 2 == 0 && n < MAXRAD) { rad[n++] = 2; k /= 2; }
+        while (k % 3 == 0 && n < MAXRAD) { rad[n++] = 3; k /= 3; }
+        while (k % 5 == 0 && n < MAXRAD) { rad[n++] = 5; k /= 5; }
+        int m = 1;
+        for (int i = 0; i < n; ++i) { ns[i] = m; magic[i] = m >= 2 ? (unsigned)((0x100000000ULL + m - 1) / m) : 0u; m *= rad[i]; }
+        if (k != 1) n = 0;
+    }
+};
+template <int KK>
+struct StaticParams {
+    static constexpr bool is_static = true;
+    static constexpr Factors<KK> F{};
+    static constexpr int K = KK, NRAD = F.n;
+    static constexpr int stride = KK + (KK >> 3) + 1;
+    static constexpr size_t per = (size_t)stride * 16;
+    static constexpr int NF = 8 * per <= 220 * 1024 ? 8 : (4 * per <= 220 * 1024 ? 4 : (2 * per <= 220 * 1024 ? 2 : 1));
+    static constexpr int TPT = (NF == 8 && 2 * (8 * per + 2048) <= 220 * 1024) ? 32 : MAXTHREADS / NF;
+    template <int s> static constexpr int rad_v = F.rad[s];
+    template <int s> static constexpr int ns_v = F.ns[s];
+    template <int s> static constexpr unsigned magic_v = F.magic[s];
+    __host__ __device__ static constexpr int K_() { return K; }
+    __host__ __device__ static constexpr int nrad_() { return NRAD; }
+    __host__ __device__ static constexpr int NF_() { return NF; }
+    __host__ __device__ static constexpr int TPT_() { return TPT; }
+    __host__ __device__ static constexpr int stride_() { return stride; }
 };
 
 __device__ __forceinline__ int padi(int i) { return i + (i >> 3); }
@@ -189,7 +235,7 @@ __device__ __forceinline__ void pass(double2* __restrict__ x, int K, int Ns, uns
 
 template <bool DIT, int IO>
 __device__ __forceinline__ void run_pass(const Params& fp, int s, double2* x, int lt, const double2* tw, double sgn, const RowIO& io) {
-    const int R = fp.rad[s], K = fp.K, Ns = fp.ns[s], tpt = fp.TPT;
+    const int R = fp.rad[s], K = fp.K, Ns = fp.ns[s], tpt = fp.TPT_();
     const unsigned magic = fp.magic[s];
     if (R == 8) pass<8, DIT, IO>(x, K, Ns, magic, tpt, lt, tw, sgn, io);
     else if (R == 4) pass<4, DIT, IO>(x, K, Ns, magic, tpt, lt, tw, sgn, io);
@@ -197,12 +243,66 @@ __device__ __forceinline__ void run_pass(const Params& fp, int s, double2* x, in
     else if (R == 3) pass<3, DIT, IO>(x, K, Ns, magic, tpt, lt, tw, sgn, io);
     else pass<5, DIT, IO>(x, K, Ns, magic, tpt, lt, tw, sgn, io);
 }
+template <class FP, bool DIT, int IO, int s>
+__device__ __forceinline__ void run_pass_c(double2* x, int lt, const double2* tw, double sgn, const RowIO& io) {
+    constexpr int R = FP::template rad_v<s>, Ns = FP::template ns_v<s>;
+    constexpr unsigned magic = FP::template magic_v<s>;
+    pass<R, DIT, IO>(x, FP::K, Ns, magic, FP::TPT, lt, tw, sgn, io);
+}
+
+// all passes of one transform.  Synthesis (DIT): passes 0 .. nrad-2 in place, the last one straight to the grid rows;
+// analysis (DIF): the first one (s = nrad-1) straight from the grid rows, then nrad-2 .. 0 in place.
+template <class FP, int s>
+__device__ __forceinline__ void syn_passes_c(double2* x, int tr, int lt, const double2* tw, const RowIO& io) {
+    if constexpr (s + 1 < FP::NRAD) {
+        run_pass_c<FP, true, 0, s>(x, lt, tw, +1.0, io);
+        group_sync(1 + tr, FP::TPT);
+        syn_passes_c<FP, s + 1>(x, tr, lt, tw, io);
+    } else {
+        run_pass_c<FP, true, 1, s>(x, lt, tw, +1.0, io);
+    }
+}
+template <class FP, int s>
+__device__ __forceinline__ void ana_passes_c(double2* x, int tr, int lt, const double2* tw, const RowIO& io) {
+    if constexpr (s == FP::NRAD - 1) run_pass_c<FP, false, 2, s>(x, lt, tw, -1.0, io);
+    else run_pass_c<FP, false, 0, s>(x, lt, tw, -1.0, io);
+    if constexpr (s > 0) {
+        group_sync(1 + tr, FP::TPT);
+        ana_passes_c<FP, s - 1>(x, tr, lt, tw, io);
+    }
+}
+template <class FP>
+__device__ __forceinline__ void syn_passes(const FP& fp, double2* x, int tr, int lt, const double2* tw, const RowIO& io) {
+    if constexpr (FP::is_static) {
+        syn_passes_c<FP, 0>(x, tr, lt, tw, io);
+    } else {
+        for (int s = 0; s + 1 < fp.nrad; ++s) {
+            run_pass<true, 0>(fp, s, x, lt, tw, +1.0, io);
+            group_sync(1 + tr, fp.TPT_());
+        }
+        run_pass<true, 1>(fp, fp.nrad - 1, x, lt, tw, +1.0, io);
+    }
+}
+template <class FP>
+__device__ __forceinline__ void ana_passes(const FP& fp, double2* x, int tr, int lt, const double2* tw, const RowIO& io) {
+    if constexpr (FP::is_static) {
+        ana_passes_c<FP, FP::NRAD - 1>(x, tr, lt, tw, io);
+    } else {
+        run_pass<false, 2>(fp, fp.nrad - 1, x, lt, tw, -1.0, io);
+        if (fp.nrad > 1) group_sync(1 + tr, fp.TPT_());
+        for (int s = fp.nrad - 2; s >= 0; --s) {
+            run_pass<false, 0>(fp, s, x, lt, tw, -1.0, io);
+            if (s > 0) group_sync(1 + tr, fp.TPT_());
+        }
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(MAXTHREADS) k_lon_syn_fft(DevTables t, Params fp, const int* __restrict__ perm, int batch, const double* __restrict__ G,
+template <class FP>
+__global__ void __launch_bounds__(MAXTHREADS) k_lon_syn_fft(DevTables t, FP fp, const int* __restrict__ perm, int batch, const double* __restrict__ G,
                                                              double* __restrict__ grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon) {
     extern __shared__ double2 smem2[];
-    const int K = fp.K, N = t.nmax, R = t.nrows, NC = t.NC, Bp = t.Bp, NF = fp.NF;
+    const int K = fp.K_(), N = t.nmax, R = t.nrows, NF = fp.NF_();
     const int row = blockIdx.y, b0 = blockIdx.x * NF;
     const int tid = threadIdx.x, NTHREADS = blockDim.x;
     const int i1 = t.row_i1[row], i2 = t.row_i2[row];
@@ -212,7 +312,7 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_syn_fft(DevTables t, Params 
     const bool simple = 2 * N <= K;                    // no aliasing: every slot is written at most once (m = K/2 folds onto itself like m = 0)
     const int fsh = 31 - __clz(NF);
     const int f = tid & (NF - 1), mstep = NTHREADS >> fsh;
-    double2* xf = smem2 + (size_t)f * fp.stride;
+    double2* xf = smem2 + (size_t)f * fp.stride_();
     const bool flive = b0 + f < batch;
     const int64_t gstep = (int64_t)R * 2 * t.Gs;       // G stride between consecutive orders
     const double* gcol = G + ((int64_t)row * 2) * t.Gs + colidx(0, b0 + f, t.GS);
@@ -222,7 +322,7 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_syn_fft(DevTables t, Params 
         if (!flive)
             for (int k = tid >> fsh; k < K; k += mstep) xf[padi(k)] = make_double2(0.0, 0.0);
     } else {
-        for (int i = tid; i < NF * fp.stride; i += NTHREADS) smem2[i] = make_double2(0.0, 0.0);
+        for (int i = tid; i < NF * fp.stride_(); i += NTHREADS) smem2[i] = make_double2(0.0, 0.0);
         __syncthreads();
     }
     const int nrounds = simple ? 1 : (N + K) / K;
@@ -271,8 +371,8 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_syn_fft(DevTables t, Params 
         }
     }
     // ---- inverse FFT (decimation in time)
-    const int tr = tid / fp.TPT, lt = tid - tr * fp.TPT;
-    double2* x = smem2 + (size_t)tr * fp.stride;
+    const int tr = tid / fp.TPT_(), lt = tid - tr * fp.TPT_();
+    double2* x = smem2 + (size_t)tr * fp.stride_();
     // the transforms of a CTA are independent from here on: per-transform named barriers let their passes and row
     // stores drift apart and overlap instead of marching in lock step
     const int b = b0 + tr;
@@ -280,25 +380,22 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_syn_fft(DevTables t, Params 
     io.live = b < batch; io.mirror = mirror; io.gs_lon = gs_lon;
     io.o1 = grid + (int64_t)b * gs_b + (int64_t)i1 * gs_lat;
     io.o2 = grid + (int64_t)b * gs_b + (int64_t)(mirror ? i2 : 0) * gs_lat;
-    for (int s = 0; s + 1 < fp.nrad; ++s) {
-        run_pass<true, 0>(fp, s, x, lt, t.tw, +1.0, io);
-        group_sync(1 + tr, fp.TPT);
-    }
-    // ---- last pass + store: real part -> primary latitude, imaginary part -> mirror latitude
-    run_pass<true, 1>(fp, fp.nrad - 1, x, lt, t.tw, +1.0, io);
+    // ---- passes; the last one stores: real part -> primary latitude, imaginary part -> mirror latitude
+    syn_passes(fp, x, tr, lt, t.tw, io);
 }
 
-__global__ void __launch_bounds__(MAXTHREADS) k_lon_ana_fft(DevTables t, Params fp, const int* __restrict__ perm, int batch, const double* __restrict__ grid,
+template <class FP>
+__global__ void __launch_bounds__(MAXTHREADS) k_lon_ana_fft(DevTables t, FP fp, const int* __restrict__ perm, int batch, const double* __restrict__ grid,
                                                              int64_t gs_b, int64_t gs_lat, int64_t gs_lon, double* __restrict__ G) {
     extern __shared__ double2 smem2[];
-    const int K = fp.K, N = t.nmax, R = t.nrows, NC = t.NC, Bp = t.Bp, NF = fp.NF;
+    const int K = fp.K_(), N = t.nmax, R = t.nrows, Bp = t.Bp, NF = fp.NF_();
     const int row = blockIdx.y, b0 = blockIdx.x * NF;
     const int tid = threadIdx.x, NTHREADS = blockDim.x;
     const int i1 = t.row_i1[row], i2 = t.row_i2[row];
     const bool mirror = i2 >= 0;
     const double w1 = t.w1[row], w2 = t.w2[row];
-    const int tr = tid / fp.TPT, lt = tid - tr * fp.TPT;
-    double2* x = smem2 + (size_t)tr * fp.stride;
+    const int tr = tid / fp.TPT_(), lt = tid - tr * fp.TPT_();
+    double2* x = smem2 + (size_t)tr * fp.stride_();
     {
         // ---- first pass straight from the grid rows (primary latitude -> real part, mirror -> imaginary part); fields past
         // the batch enter as zeros
@@ -307,12 +404,7 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_ana_fft(DevTables t, Params 
         io.live = b < batch; io.mirror = mirror; io.gs_lon = gs_lon;
         io.o1 = const_cast<double*>(grid) + (int64_t)b * gs_b + (int64_t)i1 * gs_lat;
         io.o2 = const_cast<double*>(grid) + (int64_t)b * gs_b + (int64_t)(mirror ? i2 : 0) * gs_lat;
-        run_pass<false, 2>(fp, fp.nrad - 1, x, lt, t.tw, -1.0, io);
-        if (fp.nrad > 1) group_sync(1 + tr, fp.TPT);
-        for (int s = fp.nrad - 2; s >= 0; --s) {
-            run_pass<false, 0>(fp, s, x, lt, t.tw, -1.0, io);
-            if (s > 0) group_sync(1 + tr, fp.TPT);
-        }
+        ana_passes(fp, x, tr, lt, t.tw, io);
     }
     __syncthreads();
     {
@@ -321,7 +413,7 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_ana_fft(DevTables t, Params 
         const int f = tid & (NF - 1), mstep = NTHREADS >> fsh;
         const int b = b0 + f;
         if (b < Bp) {
-            const double2* xx = smem2 + (size_t)f * fp.stride;
+            const double2* xx = smem2 + (size_t)f * fp.stride_();
             const bool live = b < batch;
             const int64_t gstep = (int64_t)R * 2 * t.Gs;
             double* gcol = G + ((int64_t)row * 2) * t.Gs + colidx(0, b, t.GS);
@@ -366,7 +458,7 @@ static bool fft_params(int K, int Bp, fft::Params& fp) {
     fp.stride = K + (K >> 3) + 1;
     // fields per CTA: as many as fit (8 = one full 128-byte line of G per order and parity); two CTAs of 4 fields per SM
     // measured no faster (r01: 0.61 vs 0.57 ms synthesis at cfg3)
-    const size_t per = (size_t)fp.stride * sizeof(double2);
+    const size_t per = (size_t)fp.stride_() * sizeof(double2);
     int nf = 0;
     for (int c = 1; c <= 8 && c <= Bp; c *= 2)
         if (c * per <= 220 * 1024) nf = c;
@@ -397,28 +489,63 @@ void lon_fft_perm(int K, int Bp, std::vector<int>& perm) {
     }
 }
 
+// longitude counts with compile-time kernels: regular grids of 1 / 0.5 / 0.25 / 0.125 degree and 5', Gauss grids of
+// nmax 96 ... 2160 (engine.py: _nice_nlon)
+#define SHB_FFT_STATIC_LENGTHS(X) X(240) X(360) X(384) X(480) X(576) X(720) X(768) X(1152) X(1440) X(1536) X(2304) X(2880) X(3072) X(4320) X(4608)
+
+template <class FP>
+static int launch_syn_fp(const Plan& p, const FP& fp, int NF, int nthreads, size_t smem, int batch, double* grid, int64_t gs_b, int64_t gs_lat,
+                         int64_t gs_lon, cudaStream_t st) {
+    static PerDeviceOnce attr;
+    if (attr.first()) { SHB_CUDA(cudaFuncSetAttribute(fft::k_lon_syn_fft<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); }
+    dim3 g((batch + NF - 1) / NF, p.nrows);
+    fft::k_lon_syn_fft<FP><<<g, nthreads, smem, st>>>(p.t, fp, p.fft_perm, batch, p.G, grid, gs_b, gs_lat, gs_lon);
+    return 0;
+}
+template <class FP>
+static int launch_ana_fp(const Plan& p, const FP& fp, int NF, int nthreads, size_t smem, int batch, const double* grid, int64_t gs_b, int64_t gs_lat,
+                         int64_t gs_lon, cudaStream_t st) {
+    static PerDeviceOnce attr;
+    if (attr.first()) { SHB_CUDA(cudaFuncSetAttribute(fft::k_lon_ana_fft<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); }
+    // field groups made of padding only are skipped: their G columns keep whatever they held (zeros after plan creation),
+    // and the Legendre stage's results for padded fields are never unpacked
+    dim3 g((batch + NF - 1) / NF, p.nrows);
+    fft::k_lon_ana_fft<FP><<<g, nthreads, smem, st>>>(p.t, fp, p.fft_perm, batch, grid, gs_b, gs_lat, gs_lon, p.G);
+    return 0;
+}
+
 int launch_lon_syn_fft(const Plan& p, int batch, double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, cudaStream_t st) {
     fft::Params fp;
     fft_params(p.K, p.Bp, fp);
-    size_t smem = (size_t)fp.NF * fp.stride * sizeof(double2);
-    static PerDeviceOnce attr;
-    if (attr.first()) { SHB_CUDA(cudaFuncSetAttribute(fft::k_lon_syn_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); }
-    dim3 g((batch + fp.NF - 1) / fp.NF, p.nrows);
-    fft::k_lon_syn_fft<<<g, fp.nthreads, smem, st>>>(p.t, fp, p.fft_perm, batch, p.G, grid, gs_b, gs_lat, gs_lon);
-    return 0;
+    const size_t smem = (size_t)fp.NF * fp.stride * sizeof(double2);
+    switch (p.K) {
+#define X(KK)                                                                                                              \
+    case KK:                                                                                                               \
+        if (fft::StaticParams<KK>::NF == fp.NF && fft::StaticParams<KK>::TPT == fp.TPT)                                    \
+            return launch_syn_fp(p, fft::StaticParams<KK>{}, fp.NF, fp.nthreads, smem, batch, grid, gs_b, gs_lat, gs_lon, st); \
+        break;
+        SHB_FFT_STATIC_LENGTHS(X)
+#undef X
+        default: break;
+    }
+    return launch_syn_fp(p, fp, fp.NF, fp.nthreads, smem, batch, grid, gs_b, gs_lat, gs_lon, st);
 }
 
 int launch_lon_ana_fft(const Plan& p, int batch, const double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, cudaStream_t st) {
     fft::Params fp;
     fft_params(p.K, p.Bp, fp);
-    size_t smem = (size_t)fp.NF * fp.stride * sizeof(double2);
-    static PerDeviceOnce attr;
-    if (attr.first()) { SHB_CUDA(cudaFuncSetAttribute(fft::k_lon_ana_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); }
-    // field groups made of padding only are skipped: their G columns keep whatever they held (zeros after plan creation),
-    // and the Legendre stage's results for padded fields are never unpacked
-    dim3 g((batch + fp.NF - 1) / fp.NF, p.nrows);
-    fft::k_lon_ana_fft<<<g, fp.nthreads, smem, st>>>(p.t, fp, p.fft_perm, batch, grid, gs_b, gs_lat, gs_lon, p.G);
-    return 0;
+    const size_t smem = (size_t)fp.NF * fp.stride * sizeof(double2);
+    switch (p.K) {
+#define X(KK)                                                                                                              \
+    case KK:                                                                                                               \
+        if (fft::StaticParams<KK>::NF == fp.NF && fft::StaticParams<KK>::TPT == fp.TPT)                                    \
+            return launch_ana_fp(p, fft::StaticParams<KK>{}, fp.NF, fp.nthreads, smem, batch, grid, gs_b, gs_lat, gs_lon, st); \
+        break;
+        SHB_FFT_STATIC_LENGTHS(X)
+#undef X
+        default: break;
+    }
+    return launch_ana_fp(p, fp, fp.NF, fp.nthreads, smem, batch, grid, gs_b, gs_lat, gs_lon, st);
 }
 
 }  // namespace shb
