@@ -14,6 +14,8 @@
 // digit-reversed slot, natural-order output -> coalesced row stores), decimation in frequency for analysis (natural
 // input, spectrum picked up from the digit-reversed slots).  NF consecutive fields of one latitude pair per CTA so that
 // every G access is a full 64 B segment.
+#include <algorithm>
+#include <cstdlib>
 #include "internal.h"
 
 namespace shb {
@@ -262,13 +264,13 @@ __device__ __forceinline__ void syn_passes_c(double2* x, int tr, int lt, const d
         run_pass_c<FP, true, 1, s>(x, lt, tw, +1.0, io);
     }
 }
-template <class FP, int s>
-__device__ __forceinline__ void ana_passes_c(double2* x, int tr, int lt, const double2* tw, const RowIO& io) {
-    if constexpr (s == FP::NRAD - 1) run_pass_c<FP, false, 2, s>(x, lt, tw, -1.0, io);
+template <class FP, int s, class Hook>
+__device__ __forceinline__ void ana_passes_c(double2* x, int tr, int lt, const double2* tw, const RowIO& io, Hook&& after_first) {
+    if constexpr (s == FP::NRAD - 1) { run_pass_c<FP, false, 2, s>(x, lt, tw, -1.0, io); after_first(); }
     else run_pass_c<FP, false, 0, s>(x, lt, tw, -1.0, io);
     if constexpr (s > 0) {
         group_sync(1 + tr, FP::TPT);
-        ana_passes_c<FP, s - 1>(x, tr, lt, tw, io);
+        ana_passes_c<FP, s - 1>(x, tr, lt, tw, io, after_first);
     }
 }
 template <class FP>
@@ -283,12 +285,13 @@ __device__ __forceinline__ void syn_passes(const FP& fp, double2* x, int tr, int
         run_pass<true, 1>(fp, fp.nrad - 1, x, lt, tw, +1.0, io);
     }
 }
-template <class FP>
-__device__ __forceinline__ void ana_passes(const FP& fp, double2* x, int tr, int lt, const double2* tw, const RowIO& io) {
+template <class FP, class Hook>
+__device__ __forceinline__ void ana_passes(const FP& fp, double2* x, int tr, int lt, const double2* tw, const RowIO& io, Hook&& after_first) {
     if constexpr (FP::is_static) {
-        ana_passes_c<FP, FP::NRAD - 1>(x, tr, lt, tw, io);
+        ana_passes_c<FP, FP::NRAD - 1>(x, tr, lt, tw, io, after_first);
     } else {
         run_pass<false, 2>(fp, fp.nrad - 1, x, lt, tw, -1.0, io);
+        after_first();
         if (fp.nrad > 1) group_sync(1 + tr, fp.TPT_());
         for (int s = fp.nrad - 2; s >= 0; --s) {
             run_pass<false, 0>(fp, s, x, lt, tw, -1.0, io);
@@ -300,7 +303,7 @@ __device__ __forceinline__ void ana_passes(const FP& fp, double2* x, int tr, int
 // ------------------------------------------------------------------------------------------------
 template <class FP>
 __global__ void __launch_bounds__(MAXTHREADS) k_lon_syn_fft(DevTables t, FP fp, const int* __restrict__ perm, int batch, const double* __restrict__ G,
-                                                             double* __restrict__ grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon) {
+                                                             double* __restrict__ grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, int pf_ahead) {
     extern __shared__ double2 smem2[];
     const int K = fp.K_(), N = t.nmax, R = t.nrows, NF = fp.NF_();
     const int row = blockIdx.y, b0 = blockIdx.x * NF;
@@ -370,6 +373,24 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_syn_fft(DevTables t, FP fp, 
             __syncthreads();
         }
     }
+    // ---- L2 prefetch for the CTA that will take this one's place: CTAs start in linear order, `ahead` of them are resident
+    // at once, so CTA L + ahead begins about when this one ends; its slab of G (one 128-byte line per order and parity at 8
+    // fields) then waits in L2 instead of DRAM when its assembly starts (ncu r01: 16 % of this kernel's samples were the
+    // first use of those loads)
+    {
+        const int64_t L = (int64_t)blockIdx.y * gridDim.x + blockIdx.x + pf_ahead;
+        const int prow = (int)(L / gridDim.x), pgrp = (int)(L - (int64_t)prow * gridDim.x);
+        if (pf_ahead > 0 && prow < R) {
+            const char* base = reinterpret_cast<const char*>(G + ((int64_t)prow * 2) * t.Gs + colidx(0, pgrp * NF, t.GS));
+            const int64_t ostep = gstep * 8, estep = (int64_t)t.Gs * 8;       // bytes between orders / parities
+            const int span = NF * 16;                                           // bytes of the group's cos+sin columns
+            for (int i = tid; i < 2 * (N + 1); i += NTHREADS) {
+                const char* a = base + (int64_t)(i >> 1) * ostep + (i & 1) * estep;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+                if (span > 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 128));
+            }
+        }
+    }
     // ---- inverse FFT (decimation in time)
     const int tr = tid / fp.TPT_(), lt = tid - tr * fp.TPT_();
     double2* x = smem2 + (size_t)tr * fp.stride_();
@@ -386,7 +407,7 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_syn_fft(DevTables t, FP fp, 
 
 template <class FP>
 __global__ void __launch_bounds__(MAXTHREADS) k_lon_ana_fft(DevTables t, FP fp, const int* __restrict__ perm, int batch, const double* __restrict__ grid,
-                                                             int64_t gs_b, int64_t gs_lat, int64_t gs_lon, double* __restrict__ G) {
+                                                             int64_t gs_b, int64_t gs_lat, int64_t gs_lon, double* __restrict__ G, int pf_ahead) {
     extern __shared__ double2 smem2[];
     const int K = fp.K_(), N = t.nmax, R = t.nrows, Bp = t.Bp, NF = fp.NF_();
     const int row = blockIdx.y, b0 = blockIdx.x * NF;
@@ -404,7 +425,22 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_ana_fft(DevTables t, FP fp, 
         io.live = b < batch; io.mirror = mirror; io.gs_lon = gs_lon;
         io.o1 = const_cast<double*>(grid) + (int64_t)b * gs_b + (int64_t)i1 * gs_lat;
         io.o2 = const_cast<double*>(grid) + (int64_t)b * gs_b + (int64_t)(mirror ? i2 : 0) * gs_lat;
-        ana_passes(fp, x, tr, lt, t.tw, io);
+        // L2 prefetch of the grid rows of the CTA that will take this one's place (see k_lon_syn_fft), issued once this
+        // transform's own row loads are done (before them it costs more than it saves: 0.40 -> 0.46 ms at cfg3)
+        auto prefetch_next = [&]() {
+            const int64_t L = (int64_t)blockIdx.y * gridDim.x + blockIdx.x + pf_ahead;
+            const int prow = (int)(L / gridDim.x), pb = (int)(L - (int64_t)prow * gridDim.x) * NF + tr;
+            if (pf_ahead > 0 && prow < R && pb < batch && gs_lon == 1) {
+                const int p1 = t.row_i1[prow], p2 = t.row_i2[prow];
+                const char* r1 = reinterpret_cast<const char*>(grid + (int64_t)pb * gs_b + (int64_t)p1 * gs_lat);
+                const char* r2 = reinterpret_cast<const char*>(grid + (int64_t)pb * gs_b + (int64_t)(p2 >= 0 ? p2 : p1) * gs_lat);
+                for (int i = lt * 128; i < K * 8; i += fp.TPT_() * 128) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(r1 + i));
+                    if (p2 >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(r2 + i));
+                }
+            }
+        };
+        ana_passes(fp, x, tr, lt, t.tw, io, prefetch_next);
     }
     __syncthreads();
     {
@@ -499,7 +535,12 @@ static int launch_syn_fp(const Plan& p, const FP& fp, int NF, int nthreads, size
     static PerDeviceOnce attr;
     if (attr.first()) { SHB_CUDA(cudaFuncSetAttribute(fft::k_lon_syn_fft<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); }
     dim3 g((batch + NF - 1) / NF, p.nrows);
-    fft::k_lon_syn_fft<FP><<<g, nthreads, smem, st>>>(p.t, fp, p.fft_perm, batch, p.G, grid, gs_b, gs_lat, gs_lon);
+    // CTAs resident at once = the prefetch distance
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fft::k_lon_syn_fft<FP>, nthreads, smem);
+    static const int pf_env = getenv("SHB200_FFT_PREFETCH") ? atoi(getenv("SHB200_FFT_PREFETCH")) : 1;
+    const int ahead = pf_env ? std::max(1, per_sm) * device_sm_count() : 0;
+    fft::k_lon_syn_fft<FP><<<g, nthreads, smem, st>>>(p.t, fp, p.fft_perm, batch, p.G, grid, gs_b, gs_lat, gs_lon, ahead);
     return 0;
 }
 template <class FP>
@@ -510,7 +551,11 @@ static int launch_ana_fp(const Plan& p, const FP& fp, int NF, int nthreads, size
     // field groups made of padding only are skipped: their G columns keep whatever they held (zeros after plan creation),
     // and the Legendre stage's results for padded fields are never unpacked
     dim3 g((batch + NF - 1) / NF, p.nrows);
-    fft::k_lon_ana_fft<FP><<<g, nthreads, smem, st>>>(p.t, fp, p.fft_perm, batch, grid, gs_b, gs_lat, gs_lon, p.G);
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fft::k_lon_ana_fft<FP>, nthreads, smem);
+    static const int pf_env = getenv("SHB200_FFT_PREFETCH") ? atoi(getenv("SHB200_FFT_PREFETCH")) : 1;
+    const int ahead = pf_env ? std::max(1, per_sm) * device_sm_count() : 0;
+    fft::k_lon_ana_fft<FP><<<g, nthreads, smem, st>>>(p.t, fp, p.fft_perm, batch, grid, gs_b, gs_lat, gs_lon, p.G, ahead);
     return 0;
 }
 
