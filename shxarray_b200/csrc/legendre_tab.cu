@@ -207,7 +207,10 @@ struct TA {
     static constexpr int RT = 32, NS = 32 * NDG, SB = 4 * NS, NCOLS = 32 * NCQ;
     static constexpr int CROW = NCOLS + 2;
     static constexpr int PSTAGES = NCQ == 1 ? 5 : 8;
-    static constexpr int NCONS = 256, NTHREADS = NCONS + 32;
+    // warps 0-7 (two warpgroups) consume, warp 8 feeds them; warps 9-11 only complete the third warpgroup so that it can
+    // hand its registers to the consumers (setmaxnreg works on whole warpgroups)
+    static constexpr int NCONS = 256, NTHREADS = 384;
+    static constexpr int REGS_CONSUMER = 232, REGS_PRODUCER = 40;
     static constexpr int GSZ = RT * 2 * CROW;         // [32 rows][E/O][grow] doubles
     static constexpr int PSZ = 2 * NDG * PT_SUB;      // 2 NDG 16-degree sub-tiles [16][34]
     static constexpr size_t SMEM = sizeof(double) * (2 * GSZ + PSTAGES * PSZ) + sizeof(uint64_t) * (2 * PSTAGES + 4);
@@ -241,7 +244,13 @@ __global__ void __launch_bounds__(TA<NCQ>::NTHREADS, 1) k_leg_ana_tab(DevTables 
     }
     __syncthreads();
 
-    if (warp == NCONS / 32) {
+    // Register reallocation: compiled for 168 registers per thread (12 warps), the accumulators alone take 128 of them and
+    // ptxas cannot keep the fragment loads of the next k-step in flight (ncu r01: 20 % of the consumers' samples wait for
+    // LDS results, while the same inner loop with small accumulators saturates the pipe, tools/dmma_feed.cu).  The third
+    // warpgroup shrinks to 40 registers and the consumers grow to 232.
+    if (warp >= NCONS / 32) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C_::REGS_PRODUCER));
+        if (warp > NCONS / 32) return;
         // ------------------------------------------------------------------ TMA warp
         const double* pbase = Ptab + t.pt_base[m] * t.RT32 * PT_SUB;
         int sidx = 0;
@@ -276,6 +285,7 @@ __global__ void __launch_bounds__(TA<NCQ>::NTHREADS, 1) k_leg_ana_tab(DevTables 
         }
     } else {
         // ------------------------------------------------------------------ consumers
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C_::REGS_CONSUMER));
         const int e = warp & 1, cq = (warp >> 1) % NCQ, dg = (warp >> 1) / NCQ;
         const int lr = lane >> 2, lk = lane & 3;
         double acc[8][4][2];
