@@ -204,7 +204,11 @@ __global__ void __launch_bounds__(TS<NWC>::NTHREADS, 1) k_leg_syn_tab(DevTables 
 template <int NCQ>
 struct TA {
     static constexpr int NDG = 4 / NCQ;
-    static constexpr int RT = 32, NS = 32 * NDG, SB = 4 * NS, NCOLS = 32 * NCQ;
+    // stages per super-block: 2 * SPB accumulator blocks of 8 degrees x 32 columns per warp (192 registers at SPB = 6, which the
+    // setmaxnreg reallocation pays for).  Every super-block is one pass over all rows of G: 128 -> 192 degrees per pass took the
+    // kernel from 0.849 to 0.831 ms at cfg3 (160: 0.833)
+    static constexpr int SPB = 6;
+    static constexpr int RT = 32, NS = 32 * NDG, SB = SPB * NS, NCOLS = 32 * NCQ;
     static constexpr int CROW = NCOLS + 2;
     static constexpr int PSTAGES = NCQ == 1 ? 5 : 8;
     // warps 0-7 (two warpgroups) consume, warp 8 feeds them; warps 9-11 only complete the third warpgroup so that it can
@@ -288,13 +292,13 @@ __global__ void __launch_bounds__(TA<NCQ>::NTHREADS, 1) k_leg_ana_tab(DevTables 
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C_::REGS_CONSUMER));
         const int e = warp & 1, cq = (warp >> 1) % NCQ, dg = (warp >> 1) / NCQ;
         const int lr = lane >> 2, lk = lane & 3;
-        double acc[8][4][2];
+        double acc[2 * C_::SPB][4][2];
         int sidx = 0;
         int prev_s = -1, prev_g = -1;   // P stage / G buffer consumed last: released after the next one has been acquired (see k_leg_syn_tab)
         for (int sb = 0; sb < nsb; ++sb) {
             const int ninner = min(SB / NS, (N - m - sb * SB + NS) / NS);
 #pragma unroll
-            for (int nb = 0; nb < 8; ++nb)
+            for (int nb = 0; nb < 2 * C_::SPB; ++nb)
 #pragma unroll
                 for (int cb = 0; cb < 4; ++cb) { acc[nb][cb][0] = 0.0; acc[nb][cb][1] = 0.0; }
             for (int rt = 0; rt < nrt; ++rt) {
@@ -344,7 +348,7 @@ __global__ void __launch_bounds__(TA<NCQ>::NTHREADS, 1) k_leg_ana_tab(DevTables 
                 }
             }
 #pragma unroll
-            for (int nb = 0; nb < 8; ++nb) {
+            for (int nb = 0; nb < 2 * C_::SPB; ++nb) {
                 const int k = sb * SB + (nb >> 1) * NS + 32 * dg + 16 * (nb & 1) + 2 * lr + e;
                 if (k > N - m) continue;
 #pragma unroll
