@@ -254,44 +254,46 @@ __device__ __forceinline__ void run_pass_c(double2* x, int lt, const double2* tw
 
 // all passes of one transform.  Synthesis (DIT): passes 0 .. nrad-2 in place, the last one straight to the grid rows;
 // analysis (DIF): the first one (s = nrad-1) straight from the grid rows, then nrad-2 .. 0 in place.
-template <class FP, int s>
+// SM = true: the boundary pass stays in shared memory too (batch-fastest grids, [lat][lon][B] as shlib lays them out:
+// the CTA then moves the 8 fields of a longitude together, 64 contiguous bytes, instead of one strided row per transform).
+template <class FP, bool SM, int s>
 __device__ __forceinline__ void syn_passes_c(double2* x, int tr, int lt, const double2* tw, const RowIO& io) {
     if constexpr (s + 1 < FP::NRAD) {
         run_pass_c<FP, true, 0, s>(x, lt, tw, +1.0, io);
         group_sync(1 + tr, FP::TPT);
-        syn_passes_c<FP, s + 1>(x, tr, lt, tw, io);
+        syn_passes_c<FP, SM, s + 1>(x, tr, lt, tw, io);
     } else {
-        run_pass_c<FP, true, 1, s>(x, lt, tw, +1.0, io);
+        run_pass_c<FP, true, SM ? 0 : 1, s>(x, lt, tw, +1.0, io);
     }
 }
-template <class FP, int s, class Hook>
+template <class FP, bool SM, int s, class Hook>
 __device__ __forceinline__ void ana_passes_c(double2* x, int tr, int lt, const double2* tw, const RowIO& io, Hook&& after_first) {
-    if constexpr (s == FP::NRAD - 1) { run_pass_c<FP, false, 2, s>(x, lt, tw, -1.0, io); after_first(); }
+    if constexpr (s == FP::NRAD - 1) { run_pass_c<FP, false, SM ? 0 : 2, s>(x, lt, tw, -1.0, io); if (!SM) after_first(); }
     else run_pass_c<FP, false, 0, s>(x, lt, tw, -1.0, io);
     if constexpr (s > 0) {
         group_sync(1 + tr, FP::TPT);
-        ana_passes_c<FP, s - 1>(x, tr, lt, tw, io, after_first);
+        ana_passes_c<FP, SM, s - 1>(x, tr, lt, tw, io, after_first);
     }
 }
-template <class FP>
+template <class FP, bool SM>
 __device__ __forceinline__ void syn_passes(const FP& fp, double2* x, int tr, int lt, const double2* tw, const RowIO& io) {
     if constexpr (FP::is_static) {
-        syn_passes_c<FP, 0>(x, tr, lt, tw, io);
+        syn_passes_c<FP, SM, 0>(x, tr, lt, tw, io);
     } else {
         for (int s = 0; s + 1 < fp.nrad; ++s) {
             run_pass<true, 0>(fp, s, x, lt, tw, +1.0, io);
             group_sync(1 + tr, fp.TPT_());
         }
-        run_pass<true, 1>(fp, fp.nrad - 1, x, lt, tw, +1.0, io);
+        run_pass<true, SM ? 0 : 1>(fp, fp.nrad - 1, x, lt, tw, +1.0, io);
     }
 }
-template <class FP, class Hook>
+template <class FP, bool SM, class Hook>
 __device__ __forceinline__ void ana_passes(const FP& fp, double2* x, int tr, int lt, const double2* tw, const RowIO& io, Hook&& after_first) {
     if constexpr (FP::is_static) {
-        ana_passes_c<FP, FP::NRAD - 1>(x, tr, lt, tw, io, after_first);
+        ana_passes_c<FP, SM, FP::NRAD - 1>(x, tr, lt, tw, io, after_first);
     } else {
-        run_pass<false, 2>(fp, fp.nrad - 1, x, lt, tw, -1.0, io);
-        after_first();
+        run_pass<false, SM ? 0 : 2>(fp, fp.nrad - 1, x, lt, tw, -1.0, io);
+        if (!SM) after_first();
         if (fp.nrad > 1) group_sync(1 + tr, fp.TPT_());
         for (int s = fp.nrad - 2; s >= 0; --s) {
             run_pass<false, 0>(fp, s, x, lt, tw, -1.0, io);
@@ -402,7 +404,24 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_syn_fft(DevTables t, FP fp, 
     io.o1 = grid + (int64_t)b * gs_b + (int64_t)i1 * gs_lat;
     io.o2 = grid + (int64_t)b * gs_b + (int64_t)(mirror ? i2 : 0) * gs_lat;
     // ---- passes; the last one stores: real part -> primary latitude, imaginary part -> mirror latitude
-    syn_passes(fp, x, tr, lt, t.tw, io);
+    if (gs_b == 1 && NF == 8) {
+        // batch-fastest grid: finish in shared memory, then thread <-> (longitude j, field f): a warp writes 4 longitudes x 64 B
+        syn_passes<FP, true>(fp, x, tr, lt, t.tw, io);
+        __syncthreads();
+        const int ff = tid & 7;
+        if (b0 + ff < batch) {
+            const double2* xs = smem2 + (size_t)ff * fp.stride_();
+            double* q1 = grid + (b0 + ff) + (int64_t)i1 * gs_lat;
+            double* q2 = grid + (b0 + ff) + (int64_t)(mirror ? i2 : 0) * gs_lat;
+            for (int j = tid >> 3; j < K; j += NTHREADS >> 3) {
+                const double2 v = xs[padi(j)];
+                q1[(int64_t)j * gs_lon] = v.x;
+                if (mirror) q2[(int64_t)j * gs_lon] = v.y;
+            }
+        }
+    } else {
+        syn_passes<FP, false>(fp, x, tr, lt, t.tw, io);
+    }
 }
 
 template <class FP>
@@ -440,7 +459,38 @@ __global__ void __launch_bounds__(MAXTHREADS) k_lon_ana_fft(DevTables t, FP fp, 
                 }
             }
         };
-        ana_passes(fp, x, tr, lt, t.tw, io, prefetch_next);
+        if (gs_b == 1 && NF == 8) {
+            // batch-fastest grid: thread <-> (longitude j, field f) loads 64 contiguous bytes per longitude into the transform
+            // buffers, then every pass runs in shared memory
+            const int ff = tid & 7;
+            const bool flive = b0 + ff < batch;
+            double2* xs = smem2 + (size_t)ff * fp.stride_();
+            const double* q1 = grid + (b0 + ff) + (int64_t)i1 * gs_lat;
+            const double* q2 = grid + (b0 + ff) + (int64_t)(mirror ? i2 : 0) * gs_lat;
+#pragma unroll 8
+            for (int j = tid >> 3; j < K; j += NTHREADS >> 3) {
+                double2 v = make_double2(0.0, 0.0);
+                if (flive) { v.x = q1[(int64_t)j * gs_lon]; if (mirror) v.y = q2[(int64_t)j * gs_lon]; }
+                xs[padi(j)] = v;
+            }
+            {   // successor prefetch for this layout: one 64-byte piece (8 fields) per longitude and row
+                const int64_t L = (int64_t)blockIdx.y * gridDim.x + blockIdx.x + pf_ahead;
+                const int prow = (int)(L / gridDim.x), pb0 = (int)(L - (int64_t)prow * gridDim.x) * NF;
+                if (pf_ahead > 0 && prow < R && pb0 < batch) {
+                    const int p1 = t.row_i1[prow], p2 = t.row_i2[prow];
+                    const double* r1 = grid + pb0 + (int64_t)p1 * gs_lat;
+                    const double* r2 = grid + pb0 + (int64_t)(p2 >= 0 ? p2 : p1) * gs_lat;
+                    for (int j = tid; j < K; j += NTHREADS) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(r1 + (int64_t)j * gs_lon));
+                        if (p2 >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(r2 + (int64_t)j * gs_lon));
+                    }
+                }
+            }
+            __syncthreads();
+            ana_passes<FP, true>(fp, x, tr, lt, t.tw, io, prefetch_next);
+        } else {
+            ana_passes<FP, false>(fp, x, tr, lt, t.tw, io, prefetch_next);
+        }
     }
     __syncthreads();
     {

@@ -281,6 +281,23 @@ def test_plan_used_below_its_max_batch(flags):
     big.clear()
 
 
+@pytest.mark.parametrize("nmax,B", [(96, 12), (200, 40)])
+def test_shlib_grid_layout_matches_batch_first(engine, nmax, B):
+    """[nlat, nlon, B] grids (shlib's own layout, synthesis.pyx:68-71: batch fastest) take the cooperative 64-byte
+    load / store path of the FFT kernels; same arithmetic as the batch-first path, so bit-identical results."""
+    import torch
+    g = sb.lonlat_grid(nmax, gtype="gauss")
+    c = torch.from_numpy(S.random_coefficients(nmax, B, kaula=False, seed=77)).cuda()
+    f_bf = engine.synthesis(c, lon=g["lon"], lat=g["lat"], nmax=nmax)
+    f_sh = engine.synthesis(c, lon=g["lon"], lat=g["lat"], nmax=nmax, layout="shlib")
+    assert tuple(f_sh.shape) == (len(g["lat"]), len(g["lon"]), B)
+    assert torch.equal(f_sh.permute(2, 0, 1), f_bf)
+    a_bf = engine.analysis(f_bf, nmax, g["lon"], g["lat"], quadrature="gauss")
+    a_sh = engine.analysis(f_sh, nmax, g["lon"], g["lat"], quadrature="gauss", layout="shlib")
+    assert torch.equal(a_sh, a_bf)
+    assert per_field_err(a_sh.cpu().numpy(), c.cpu().numpy()) <= TOL
+
+
 def test_edge_cases(engine):
     # nmax = 0, single latitude, single field; odd sizes; batch not a multiple of the column block
     out = engine.synthesis(np.array([[2.5]]), np.array([0]), np.array([0]), [10.0, 20.0, 30.0], [5.0])
