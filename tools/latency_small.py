@@ -1,4 +1,5 @@
-import sys, time; sys.path.insert(0, '/root/repo')
+"""Wall-clock and enqueue cost per engine call for the launch-latency-bound configs (cfg1, cfg5): host side vs GPU side."""
+import os, sys, time; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import shxarray_b200 as sb
 from shxarray_b200 import synthetic as S

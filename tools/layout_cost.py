@@ -1,4 +1,5 @@
-import sys; sys.path.insert(0, '/root/repo')
+"""cfg3 with batch-first grids against shlib's batch-fastest [nlat, nlon, B] layout (device-resident, CUDA events)."""
+import os, sys; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import shxarray_b200 as sb
 from shxarray_b200 import synthetic as S
