@@ -291,11 +291,20 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
         if (need_mib <= budget_mib) {
             if ((rc = upload(p, ptb, &t.pt_base))) return rc;
             t.RT32 = p.Rpad / 32;
-            if ((rc = dev_alloc(p, sizeof(double) * pt_elems, &ptr))) return rc;
-            p.Ptab = (double*)ptr;
-            SHB_CUDA(cudaMemset(p.Ptab, 0, sizeof(double) * pt_elems));
-            launch_ptab_gen(p, 0);
-            SHB_CUDA(cudaDeviceSynchronize());
+            // the table is an accelerator, not a requirement: if the allocation fails after all (fragmentation, another
+            // process took the memory) the plan falls back to the fused-recursion kernels
+            void* tab = nullptr;
+            if (cudaMalloc(&tab, sizeof(double) * pt_elems) == cudaSuccess) {
+                p.owned.push_back(tab);
+                p.workspace_bytes += sizeof(double) * pt_elems;
+                p.Ptab = (double*)tab;
+                SHB_CUDA(cudaMemset(p.Ptab, 0, sizeof(double) * pt_elems));
+                launch_ptab_gen(p, 0);
+                SHB_CUDA(cudaDeviceSynchronize());
+            } else {
+                cudaGetLastError();      // clear the allocation error
+                t.RT32 = 0;
+            }
         }
     }
     if (d.flags & SHB200_FLAG_TIMING)
