@@ -180,16 +180,31 @@ class SHEngine:
         flags = self.flags if flags is None else flags
         maxb = self._chunk(nmax, len(lat), batch)
         key = (nmax, mode, quadrature, float(weight), flags, _digest(lat, lon, n, m, lat_weights))
+        # same grid and nm list, whatever the quadrature: a plan made for analysis also runs synthesis (the weights only
+        # enter the analysis longitude stage), so a round trip on one grid needs ONE plan -- one workspace, one P table
+        # (20 GB at nmax 2160 on the 5' grid)
+        gkey = (nmax, mode, flags, _digest(lat, lon, n, m))
         with self._lock:
             plan = self._plans.get(key)
             if plan is not None and plan.max_batch >= maxb:
                 self._plans.move_to_end(key)
                 return plan
+            if plan is None and quadrature == capi.QUAD_NONE:
+                for k2, p2 in self._plans.items():
+                    if getattr(p2, "_gkey", None) == gkey and p2.max_batch >= maxb:
+                        self._plans.move_to_end(k2)
+                        return p2
             if plan is not None:
                 del self._plans[key]
                 plan.close()
+            if quadrature != capi.QUAD_NONE:
+                # the new plan supersedes synthesis-only plans of the same grid that are not larger
+                for k2 in [k2 for k2, p2 in self._plans.items()
+                           if k2[2] == capi.QUAD_NONE and getattr(p2, "_gkey", None) == gkey and p2.max_batch <= maxb]:
+                    self._plans.pop(k2).close()
             plan = capi.Plan(nmax, lat, lon, max_batch=maxb, n=n, m=m, mode=mode, quadrature=quadrature,
                              weight=weight, lat_weights=lat_weights, flags=flags, device=self.device)
+            plan._gkey = gkey
             self._plans[key] = plan
             # least-recently-used eviction (a plan owns its workspace and, for tensor-core plans, a P_nm table)
             total = sum(int(q.info.workspace_bytes) for q in self._plans.values())

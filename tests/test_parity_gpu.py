@@ -298,6 +298,30 @@ def test_shlib_grid_layout_matches_batch_first(engine, nmax, B):
     assert per_field_err(a_sh.cpu().numpy(), c.cpu().numpy()) <= TOL
 
 
+def test_round_trip_on_one_grid_shares_one_plan():
+    """Synthesis and analysis on the same grid (full nm triangle) run on ONE plan -- one workspace, one P table: the analysis
+    plan supersedes the synthesis-only plan made first, later syntheses reuse it; results are those of separate plans."""
+    import torch
+    nmax, B = 150, 20
+    g = sb.lonlat_grid(nmax, gtype="gauss")
+    c = torch.from_numpy(S.random_coefficients(nmax, B, kaula=False, seed=3)).cuda()
+    eng = sb.SHEngine(0)
+    f1 = eng.synthesis(c, lon=g["lon"], lat=g["lat"], nmax=nmax)
+    assert len(eng._plans) == 1
+    a = eng.analysis(f1, nmax, g["lon"], g["lat"], quadrature="gauss")
+    assert len(eng._plans) == 1                      # the synthesis-only plan was superseded
+    f2 = eng.synthesis(c, lon=g["lon"], lat=g["lat"], nmax=nmax)
+    assert len(eng._plans) == 1 and torch.equal(f1, f2)
+    num = (a - c).abs().amax(dim=1); den = c.abs().amax(dim=1)
+    assert float((num / den).max()) <= TOL
+    # a subset nm list is a different transform: its own plan
+    n, m = sb.nm_index(nmax)
+    keep = n >= 2
+    eng.synthesis(c[:, torch.from_numpy(keep).cuda()], n[keep], m[keep], g["lon"], g["lat"])
+    assert len(eng._plans) == 2
+    eng.clear()
+
+
 def test_edge_cases(engine):
     # nmax = 0, single latitude, single field; odd sizes; batch not a multiple of the column block
     out = engine.synthesis(np.array([[2.5]]), np.array([0]), np.array([0]), [10.0, 20.0, 30.0], [5.0])
