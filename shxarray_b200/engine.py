@@ -153,6 +153,18 @@ def _digest(*arrays):
     return h.hexdigest()
 
 
+_std_nm = {}
+
+
+def _std_nm_digest(nmax):
+    if nmax not in _std_nm:
+        if len(_std_nm) > 32:
+            _std_nm.clear()
+        n, m = nm_index(nmax)
+        _std_nm[nmax] = _digest(np.ascontiguousarray(n, dtype=np.int32), np.ascontiguousarray(m, dtype=np.int32))
+    return _std_nm[nmax]
+
+
 class SHEngine:
     """Plan cache + array front-end.  One instance per process/device is enough (plans are reused)."""
 
@@ -179,6 +191,12 @@ class SHEngine:
                  weight=0.0, lat_weights=None, flags=None):
         flags = self.flags if flags is None else flags
         maxb = self._chunk(nmax, len(lat), batch)
+        if n is not None and len(n) == (nmax + 1) ** 2:
+            # an explicit nm list that is the full triangle in standard order (what the xarray accessor passes) is the
+            # default list: same plan as for n = None
+            std = _std_nm_digest(nmax)
+            if _digest(np.ascontiguousarray(n, dtype=np.int32), np.ascontiguousarray(m, dtype=np.int32)) == std:
+                n = m = None
         key = (nmax, mode, quadrature, float(weight), flags, _digest(lat, lon, n, m, lat_weights))
         # same grid and nm list, whatever the quadrature: a plan made for analysis also runs synthesis (the weights only
         # enter the analysis longitude stage), so a round trip on one grid needs ONE plan -- one workspace, one P table

@@ -314,8 +314,11 @@ def test_round_trip_on_one_grid_shares_one_plan():
     assert len(eng._plans) == 1 and torch.equal(f1, f2)
     num = (a - c).abs().amax(dim=1); den = c.abs().amax(dim=1)
     assert float((num / den).max()) <= TOL
-    # a subset nm list is a different transform: its own plan
+    # the explicit full-triangle list (what the xarray accessor passes) is the default list: still one plan
     n, m = sb.nm_index(nmax)
+    f3 = eng.synthesis(c, n, m, g["lon"], g["lat"])
+    assert len(eng._plans) == 1 and torch.equal(f1, f3)
+    # a subset nm list is a different transform: its own plan
     keep = n >= 2
     eng.synthesis(c[:, torch.from_numpy(keep).cuda()], n[keep], m[keep], g["lon"], g["lat"])
     assert len(eng._plans) == 2
