@@ -8,6 +8,7 @@ device in one call (the per-field Python loop of shtns.py:255-259 is what this e
 * torch CUDA tensors -> ``shb200_synthesis`` / ``shb200_analysis`` on torch's current stream; torch is
   used purely as the owner of device memory.
 """
+import functools
 import hashlib
 import threading
 from collections import OrderedDict
@@ -17,11 +18,21 @@ import numpy as np
 from . import capi
 
 
+@functools.lru_cache(maxsize=16)
+def _nm_index_cached(nmax, nmin):
+    k = np.arange(nmin, nmax + 1, dtype=np.int64)
+    n = np.repeat(k, 2 * k + 1).astype(np.int32)
+    start = np.repeat(np.cumsum(2 * k + 1) - (2 * k + 1), 2 * k + 1)          # position of (n, -n) in the list
+    m = (np.arange(len(n), dtype=np.int64) - start - n).astype(np.int32)
+    n.setflags(write=False)
+    m.setflags(write=False)
+    return n, m
+
+
 def nm_index(nmax, nmin=0):
     """(n, m) int32 arrays in shxarray's nm order: n-major, m=-n..n (sh_indexing.py:66)."""
-    n = np.concatenate([np.full(2 * k + 1, k, dtype=np.int32) for k in range(nmin, nmax + 1)])
-    m = np.concatenate([np.arange(-k, k + 1, dtype=np.int32) for k in range(nmin, nmax + 1)])
-    return n, m
+    n, m = _nm_index_cached(int(nmax), int(nmin))
+    return n.copy(), m.copy()
 
 
 def _nice_nlon(nmin):
@@ -33,6 +44,21 @@ def _nice_nlon(nmin):
             k *= 2
         best = k if best is None or k < best else best
     return best
+
+
+@functools.lru_cache(maxsize=16)
+def _gauss_grid_cached(nmax):
+    """Gauss-Legendre grid of nmax (the nodes cost O(nlat^2) long-double operations: 10 ms at nmax 720)."""
+    nlat = (nmax + 1 + 3) // 4 * 4
+    nlon = _nice_nlon(2 * nmax + 2)
+    x, w = capi.gauss_nodes(nlat)
+    latv = np.rad2deg(np.arcsin(x))
+    half = nlat // 2
+    latv[nlat - half:] = -latv[:half][::-1]   # bit-exact mirror symmetry
+    lonv = np.arange(nlon) * (360.0 / nlon)
+    for a in (lonv, latv, w):
+        a.setflags(write=False)
+    return lonv, latv, w
 
 
 def lonlat_grid(nmax=None, lon=None, lat=None, gtype=None):
@@ -54,13 +80,8 @@ def lonlat_grid(nmax=None, lon=None, lat=None, gtype=None):
             lat = np.arange(-90 + idres / 2, 90, idres)
             return dict(lon=lon, lat=lat, gtype=gtype)
         if gtype == "gauss":
-            nlat = (nmax + 1 + 3) // 4 * 4
-            nlon = _nice_nlon(2 * nmax + 2)
-            x, w = capi.gauss_nodes(nlat)
-            latv = np.rad2deg(np.arcsin(x))
-            half = nlat // 2
-            latv[nlat - half:] = -latv[:half][::-1]   # bit-exact mirror symmetry
-            return dict(lon=np.arange(nlon) * (360.0 / nlon), lat=latv, gtype=gtype, lat_weights=w)
+            lonv, latv, w = _gauss_grid_cached(int(nmax))
+            return dict(lon=lonv.copy(), lat=latv.copy(), gtype=gtype, lat_weights=w.copy())
         raise ValueError("a 'point' grid needs explicit lon and lat")
     if lon is None or lat is None:
         raise ValueError("Either nmax or lon and lat should be specified")
@@ -160,7 +181,7 @@ def _std_nm_digest(nmax):
     if nmax not in _std_nm:
         if len(_std_nm) > 32:
             _std_nm.clear()
-        n, m = nm_index(nmax)
+        n, m = _nm_index_cached(int(nmax), 0)
         _std_nm[nmax] = _digest(np.ascontiguousarray(n, dtype=np.int32), np.ascontiguousarray(m, dtype=np.int32))
     return _std_nm[nmax]
 
@@ -416,8 +437,7 @@ class SHEngine:
         Returns [B, (nmax_a+nmax_b+1)^2]."""
         import torch
         nmax = int(nmax_a) + int(nmax_b)
-        g = lonlat_grid(nmax, gtype="gauss")
-        lon, lat, lw = g["lon"], g["lat"], g["lat_weights"]
+        lon, lat, lw = _gauss_grid_cached(nmax)
         host = not _is_torch(coef_a)
         dev = torch.device("cuda", self.device)
         ta = torch.as_tensor(np.ascontiguousarray(coef_a), device=dev) if host else coef_a
@@ -425,8 +445,8 @@ class SHEngine:
         if ta.ndim == 1:
             ta, tb = ta[None], tb[None]
         B = ta.shape[0]
-        na, ma = nm_index(nmax_a)
-        nb_, mb = nm_index(nmax_b)
+        na, ma = _nm_index_cached(int(nmax_a), 0)
+        nb_, mb = _nm_index_cached(int(nmax_b), 0)
         pa = self.get_plan(int(nmax_a), lat, lon, B, n=na, m=ma)
         pb = pa if nmax_a == nmax_b else self.get_plan(int(nmax_b), lat, lon, B, n=nb_, m=mb)
         pc = self.get_plan(nmax, lat, lon, B, quadrature=capi.QUAD_LATWEIGHTS, weight=1.0 / (2.0 * len(lon)), lat_weights=lw)
