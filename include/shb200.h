@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SHB200_VERSION 100
+#define SHB200_VERSION 200
 
 enum { SHB200_OK = 0, SHB200_EINVAL = -1, SHB200_ECUDA = -2, SHB200_ENOMEM = -3, SHB200_EUNSUPPORTED = -4 };
 
@@ -79,6 +79,26 @@ typedef struct shb200_plan_info {
     int32_t launches_analysis;   /* kernels launched per analysis call */
 } shb200_plan_info;
 
+/* Per-call options of the four transform entry points (NULL = defaults).  Nothing a call changes is kept on the plan:
+ * plans are immutable after creation and may be shared by threads (calls on one plan are serialised by a per-plan mutex
+ * for the duration of the launch sequence; the plan's workspace is handed from stream to stream through an event).
+ *   degree_scale : fused isotropic kernel: per-degree factor applied while the coefficients are packed
+ *                  (synthesis input) or unpacked (analysis output) -- what shxarray's isotropic operators do on the host
+ *                  before/after a transform (Gaussian filter, gravity functionals stokes<->tws/geoid/uplift:
+ *                  IsoKernelBase.__call__ src/shxarray/kernels/isokernelbase.py:75-92).  HOST array of nmax+1 doubles indexed
+ *                  by degree, copied by the call.  c*scale[n] is one IEEE multiplication, bit-identical to scaling first.
+ *   shard_rank/world : multi-GPU m-order sharding of ANALYSIS: integrate only the orders
+ *                  m = rank, rank+world, ... (interleaved: work per order is proportional to nmax-m+1) and write exact
+ *                  zeros for every other coefficient, so that gathering (or summing) the outputs of the `world` ranks
+ *                  gives the full result bit-identically to the unsharded transform.  world <= 1: off.  Ignored by synthesis. */
+typedef struct shb200_call_opts {
+    int32_t struct_size;        /* = sizeof(shb200_call_opts) */
+    int32_t shard_rank;
+    int32_t shard_world;
+    int32_t reserved;
+    const double* degree_scale;
+} shb200_call_opts;
+
 int shb200_version(void);
 const char* shb200_last_error(void);
 
@@ -91,19 +111,10 @@ int shb200_plan_get_info(const shb200_plan* plan, shb200_plan_info* info);
  * the launching stream; the call synchronises that stream's last event.  Used by bench.py for the roofline. */
 int shb200_plan_stage_times(shb200_plan* plan, double* ms, int32_t n);
 
-/* Fused isotropic kernel: per-degree scale applied while the coefficients are packed (which=0,
- * synthesis input) or unpacked (which=1, analysis output).  This is what shxarray's isotropic operators do on the host
- * before/after a transform -- Gaussian filter, gravity functionals stokes<->tws/geoid/uplift: IsoKernelBase.__call__
- * src/shxarray/kernels/isokernelbase.py:75-92 (dain * expanddiag(nm)).  scale: host array of nmax+1 doubles indexed by degree,
- * copied by the call; NULL switches the scale off.  The product c*scale[n] is one IEEE multiplication, i.e. bit-identical to
- * scaling on the host first. */
-int shb200_plan_set_degree_scale(shb200_plan* plan, int32_t which, const double* scale, int32_t n);
-
-/* Multi-GPU m-order sharding of ANALYSIS: the plan integrates only the orders m = rank, rank+world,
- * rank+2*world, ... (interleaved: work per order is proportional to nmax-m+1) and writes exact zeros for every other
- * coefficient, so that summing (or gathering) the outputs of the `world` ranks gives the full result bit-identically to the
- * unsharded transform.  rank=0, world=1 restores the default.  Synthesis is unaffected (it shards by latitude or batch). */
-int shb200_plan_set_order_shard(shb200_plan* plan, int32_t rank, int32_t world);
+/* Comma-separated names of the kernels launched by the most recent transform call on this plan (tests and smoke() assert
+ * the kernel family -- e.g. "k_pack_n,k_leg_syn_tab<4>,k_lon_syn_fft" -- so that a silent fallback cannot pass).  Copies at most
+ * n-1 characters + NUL into buf; returns the full length. */
+int shb200_plan_last_kernels(const shb200_plan* plan, char* buf, int32_t n);
 
 /* Synthesis  f(b, point) = sum_k C(b,k) * Ybar_{n_k m_k}(point)      [synthesis.pyx:175-189]
  *   coef element (b,k)          at coef[b*cs_b + k*cs_nm]             (device pointer, element strides)
@@ -112,21 +123,43 @@ int shb200_plan_set_order_shard(shb200_plan* plan, int32_t rank, int32_t world);
  * than the plan was made for works on the leading 2*ceil8(batch) columns of the plan's workspace only, so its cost follows
  * `batch`, not `max_batch`.  A plan serves one stream at a time (its workspace is shared by consecutive calls). */
 int shb200_synthesis(shb200_plan* plan, int32_t batch, const double* coef, int64_t cs_b, int64_t cs_nm,
-                     double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, void* stream);
+                     double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, void* stream, const shb200_call_opts* opts);
 
 /* Analysis  C(b, n^2+n+m) = sum_ij w_i * Ybar_nm(lon_j, lat_i) * f(b,i,j)   [analysis.pyx:125-139]
  *   output is always the full triangle nmin=0 in nm order (analysis.pyx:29), element (b,k) at coef[b*cs_b + k*cs_nm]. */
 int shb200_analysis(shb200_plan* plan, int32_t batch, const double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon,
-                    double* coef, int64_t cs_b, int64_t cs_nm, void* stream);
+                    double* coef, int64_t cs_b, int64_t cs_nm, void* stream, const shb200_call_opts* opts);
 
 /* Same two calls on HOST buffers: host->device copy, transform, device->host copy, synchronous.
- * This is the call the reference-facing plugin makes for numpy-backed DataArrays.  When the batch axis is the slowest
- * axis of both arrays, batches of >= 16 fields are cut into up to 4 chunks that overlap copy-in, kernels and copy-out on
- * three streams (pinned host memory is needed for the copies to be asynchronous; pageable memory works, without overlap). */
+ * This is the call the reference-facing plugin makes for numpy-backed DataArrays.  Any non-negative element strides.
+ *   - Only the elements the call owns are read / written: arrays with holes (a strided `out=` view, one chunk of a
+ *     batch-fastest array) are gathered / scattered run by run, never copied as a flat span.
+ *   - Page-locked buffers (cudaHostAlloc / cudaHostRegister / shb200_host_alloc) are DMA-ed directly; pageable memory
+ *     goes through a ring of pinned bounce buffers filled / drained by a small team of host threads
+ *     (SHB200_HOST_THREADS, default 4) so that host memcpy, H2D, kernels and D2H overlap.
+ *   - When the batch axis is the slowest axis of both arrays, batches of >= 16 fields are cut into up to 4 chunks that
+ *     flow through three streams (copy-in, kernels, copy-out): both PCIe directions run at once. */
 int shb200_synthesis_host(shb200_plan* plan, int32_t batch, const double* coef, int64_t cs_b, int64_t cs_nm,
-                          double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon);
+                          double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, const shb200_call_opts* opts);
 int shb200_analysis_host(shb200_plan* plan, int32_t batch, const double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon,
-                         double* coef, int64_t cs_b, int64_t cs_nm);
+                         double* coef, int64_t cs_b, int64_t cs_nm, const shb200_call_opts* opts);
+
+/* Synthesis and analysis of the same batch in ONE call: coef -> grid (delivered to the host array `grid`) -> coef_out.
+ * Equivalent to shb200_synthesis_host followed by shb200_analysis_host on `grid` -- the analysis input is read back from
+ * the host array, so the bytes on the wire are those of the two calls -- but software-pipelined over chunks of the batch so
+ * that the grid of chunk k+1 travels to the host while the grid of chunk k travels back (both PCIe directions busy).
+ * `grid` must be page-locked (shb200_host_alloc / cudaHostRegister); the plan needs quadrature weights. */
+int shb200_roundtrip_host(shb200_plan* plan, int32_t batch, const double* coef, int64_t cs_b, int64_t cs_nm,
+                          double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon,
+                          double* coef_out, int64_t os_b, int64_t os_nm,
+                          const shb200_call_opts* syn_opts, const shb200_call_opts* ana_opts);
+
+/* Page-locked host memory from the library's pool (cudaHostAlloc, portable).  The engine hands its numpy OUTPUT arrays out
+ * of this pool so that results are DMA-ed straight into the array the caller receives (no bounce copy, no first-touch page
+ * faults); blocks go back to the pool with shb200_host_free and are reused.  shb200_host_trim releases cached blocks. */
+int shb200_host_alloc(int64_t bytes, void** out);
+int shb200_host_free(void* ptr);
+int shb200_host_trim(void);
 
 /* Fused round trip used by engine.multiply (shtns.py:394-420 / shlib.pyx:140-152):
  *   out = analysis_planA( synthesis_planS(a) * synthesis_planS(b) )  with the grids kept on the device. */
@@ -140,6 +173,12 @@ int shb200_gauss_nodes(int32_t n, double* x, double* w);
 /* Debug/test hook: normalised P_nm table for one latitude computed by the DEVICE recursion,
  * packed like Legendre_nm.hpp:25-29 ((nmax+1)(nmax+2)/2 doubles, host pointer). */
 int shb200_debug_legendre(int32_t device, int32_t nmax, double lat_deg, double* pnm_host);
+
+/* Debug/test hook (host only, no GPU): copies a strided host array (nax <= 3 axes, extents `ext`, element strides) to its
+ * dense image (to_dense != 0) or back, through the same layout analysis, run decomposition and thread team the host entry
+ * points use for pageable memory.  info (optional, 10 values): merged dims, run length, elements, nested?, DMA-able?, span,
+ * outermost axis, dense stride of each axis. */
+int shb200_debug_host_copy(int32_t nax, const int64_t* ext, const int64_t* strides, double* host, double* dense, int32_t to_dense, int64_t* info);
 
 #ifdef __cplusplus
 }

@@ -21,8 +21,10 @@ FLAG_NO_SYMMETRY, FLAG_DENSE_LON, FLAG_NO_DMMA, FLAG_TIMING, FLAG_NO_PTABLE = 1,
 EXPORTS = [
     "shb200_version", "shb200_last_error", "shb200_plan_create", "shb200_plan_destroy", "shb200_plan_get_info",
     "shb200_synthesis", "shb200_analysis", "shb200_synthesis_host", "shb200_analysis_host", "shb200_multiply",
-    "shb200_gauss_nodes", "shb200_debug_legendre", "shb200_plan_stage_times", "shb200_plan_set_degree_scale", "shb200_plan_set_order_shard",
+    "shb200_gauss_nodes", "shb200_debug_legendre", "shb200_plan_stage_times", "shb200_plan_last_kernels", "shb200_roundtrip_host",
+    "shb200_host_alloc", "shb200_host_free", "shb200_host_trim", "shb200_debug_host_copy",
 ]
+VERSION = 200
 
 
 class PlanDesc(C.Structure):
@@ -43,6 +45,12 @@ class PlanInfo(C.Structure):
         ("nsh", C.c_int64), ("nsh_full", C.c_int64), ("workspace_bytes", C.c_int64),
         ("launches_synthesis", C.c_int32), ("launches_analysis", C.c_int32),
     ]
+
+
+class CallOpts(C.Structure):
+    """shb200_call_opts: what ONE call may change (nothing is kept on the plan)."""
+    _fields_ = [("struct_size", C.c_int32), ("shard_rank", C.c_int32), ("shard_world", C.c_int32), ("reserved", C.c_int32),
+                ("degree_scale", C.c_void_p)]
 
 
 class SHB200Error(RuntimeError):
@@ -74,20 +82,27 @@ def lib():
     L.shb200_plan_destroy.argtypes = [vp]
     L.shb200_plan_destroy.restype = None
     L.shb200_plan_get_info.argtypes = [vp, C.POINTER(PlanInfo)]
-    L.shb200_synthesis.argtypes = [vp, i32, vp, i64, i64, vp, i64, i64, i64, vp]
-    L.shb200_analysis.argtypes = [vp, i32, vp, i64, i64, i64, vp, i64, i64, vp]
-    L.shb200_synthesis_host.argtypes = [vp, i32, vp, i64, i64, vp, i64, i64, i64]
-    L.shb200_analysis_host.argtypes = [vp, i32, vp, i64, i64, i64, vp, i64, i64]
+    po = C.POINTER(CallOpts)
+    L.shb200_synthesis.argtypes = [vp, i32, vp, i64, i64, vp, i64, i64, i64, vp, po]
+    L.shb200_analysis.argtypes = [vp, i32, vp, i64, i64, i64, vp, i64, i64, vp, po]
+    L.shb200_synthesis_host.argtypes = [vp, i32, vp, i64, i64, vp, i64, i64, i64, po]
+    L.shb200_analysis_host.argtypes = [vp, i32, vp, i64, i64, i64, vp, i64, i64, po]
+    L.shb200_roundtrip_host.argtypes = [vp, i32, vp, i64, i64, vp, i64, i64, i64, vp, i64, i64, po, po]
+    L.shb200_plan_last_kernels.argtypes = [vp, C.c_char_p, i32]
+    L.shb200_host_alloc.argtypes = [i64, C.POINTER(vp)]
+    L.shb200_host_free.argtypes = [vp]
+    L.shb200_host_trim.argtypes = []
+    L.shb200_debug_host_copy.argtypes = [i32, vp, vp, vp, vp, i32, vp]
     L.shb200_multiply.argtypes = [vp, vp, vp, i32, vp, i64, i64, vp, i64, i64, vp, i64, i64, vp]
     L.shb200_plan_stage_times.argtypes = [vp, vp, i32]
-    L.shb200_plan_set_degree_scale.argtypes = [vp, i32, vp, i32]
-    L.shb200_plan_set_order_shard.argtypes = [vp, i32, i32]
     L.shb200_gauss_nodes.argtypes = [i32, vp, vp]
     L.shb200_debug_legendre.argtypes = [i32, i32, dbl, vp]
     for name in EXPORTS:
         f = getattr(L, name)
         if name not in ("shb200_last_error", "shb200_plan_destroy"):
             f.restype = C.c_int
+    if L.shb200_version() != VERSION:
+        raise SHB200Error(f"{LIB_PATH} is version {L.shb200_version()}, this binding needs {VERSION}: rebuild it (make -C shxarray_b200/csrc)")
     _lib = L
     return L
 
@@ -98,6 +113,55 @@ def check(rc):
         if rc == EINVAL:
             raise ValueError(f"shb200: {msg}")
         raise SHB200Error(f"shb200 error {rc}: {msg}")
+
+
+def _opts(degree_scale=None, order_shard=None, nmax=None):
+    """(CallOpts or None, keep-alive).  degree_scale: nmax+1 per-degree factors; order_shard: (rank, world)."""
+    if degree_scale is None and order_shard is None:
+        return None, None
+    o = CallOpts()
+    o.struct_size = C.sizeof(CallOpts)
+    keep = None
+    if degree_scale is not None:
+        keep = np.ascontiguousarray(degree_scale, dtype=np.float64)
+        if nmax is not None and len(keep) != nmax + 1:
+            raise ValueError(f"degree_scale needs nmax+1 = {nmax + 1} entries, got {len(keep)}")
+        o.degree_scale = keep.ctypes.data
+    if order_shard is not None:
+        o.shard_rank, o.shard_world = int(order_shard[0]), int(order_shard[1])
+    return o, keep
+
+
+class _PinnedBlock:
+    """Owner of one block of the library's page-locked host pool; numpy arrays made from it keep it alive (``.base``)."""
+
+    def __init__(self, nbytes):
+        self.ptr = C.c_void_p()
+        check(lib().shb200_host_alloc(int(nbytes), C.byref(self.ptr)))
+        self.nbytes = int(nbytes)
+        self.__array_interface__ = {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr.value, False), "version": 3}
+
+    def __del__(self):
+        try:
+            if self.ptr.value:
+                lib().shb200_host_free(self.ptr)
+                self.ptr = C.c_void_p()
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array in page-locked host memory from the library's pool (shb200_host_alloc): transforms DMA straight into /
+    out of it.  The block returns to the pool when the last view of the array is garbage collected."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    blk = _PinnedBlock(max(n, 1))
+    return np.asarray(blk)[:n].view(dtype).reshape(shape)
+
+
+def host_trim():
+    """Release the cached (free) blocks of the page-locked pool."""
+    check(lib().shb200_host_trim())
 
 
 def gauss_nodes(n):
@@ -190,33 +254,38 @@ class Plan:
         """self = synthesis plan of operand a; syn_b = synthesis plan of operand b; ana = analysis plan (same grid)."""
         check(lib().shb200_multiply(self._h, syn_b._h, ana._h, batch, a_ptr, as_b, as_nm, b_ptr, bs_b, bs_nm, out_ptr, os_b, os_nm, stream))
 
-    def set_degree_scale(self, which, scale):
-        """which: 0 = synthesis input, 1 = analysis output; scale: nmax+1 per-degree factors or None to switch off."""
-        if scale is None:
-            check(lib().shb200_plan_set_degree_scale(self._h, int(which), None, 0))
-        else:
-            s = np.ascontiguousarray(scale, dtype=np.float64)
-            check(lib().shb200_plan_set_degree_scale(self._h, int(which), s.ctypes.data, len(s)))
-
-    def set_order_shard(self, rank=0, world=1):
-        """analysis integrates only orders m = rank (mod world); other coefficients come out as exact zeros."""
-        check(lib().shb200_plan_set_order_shard(self._h, int(rank), int(world)))
-
     def stage_times(self):
         """dict of per-stage device ms of the last synthesis/analysis (plan needs FLAG_TIMING)."""
         ms = np.zeros(6)
         check(lib().shb200_plan_stage_times(self._h, ms.ctypes.data, 6))
         return dict(syn_pack=ms[0], syn_legendre=ms[1], syn_lon=ms[2], ana_lon=ms[3], ana_legendre=ms[4], ana_unpack=ms[5])
 
-    # raw calls: pointers are integers (device or host addresses), strides in elements
-    def synthesis_dev(self, batch, coef_ptr, cs_b, cs_nm, grid_ptr, gs_b, gs_lat, gs_lon, stream=0):
-        check(lib().shb200_synthesis(self._h, batch, coef_ptr, cs_b, cs_nm, grid_ptr, gs_b, gs_lat, gs_lon, stream))
+    def last_kernels(self):
+        """names of the kernels the most recent transform call on this plan launched, in launch order"""
+        buf = C.create_string_buffer(512)
+        lib().shb200_plan_last_kernels(self._h, buf, 512)
+        return [k for k in buf.value.decode().split(",") if k]
 
-    def analysis_dev(self, batch, grid_ptr, gs_b, gs_lat, gs_lon, coef_ptr, cs_b, cs_nm, stream=0):
-        check(lib().shb200_analysis(self._h, batch, grid_ptr, gs_b, gs_lat, gs_lon, coef_ptr, cs_b, cs_nm, stream))
+    # raw calls: pointers are integers (device or host addresses), strides in elements.  degree_scale / order_shard are
+    # per-call options (shb200_call_opts): nothing sticks to the plan.
+    def synthesis_dev(self, batch, coef_ptr, cs_b, cs_nm, grid_ptr, gs_b, gs_lat, gs_lon, stream=0, degree_scale=None):
+        o, keep = _opts(degree_scale, None, self.nmax)
+        check(lib().shb200_synthesis(self._h, batch, coef_ptr, cs_b, cs_nm, grid_ptr, gs_b, gs_lat, gs_lon, stream, o))
 
-    def synthesis_host(self, batch, coef_ptr, cs_b, cs_nm, grid_ptr, gs_b, gs_lat, gs_lon):
-        check(lib().shb200_synthesis_host(self._h, batch, coef_ptr, cs_b, cs_nm, grid_ptr, gs_b, gs_lat, gs_lon))
+    def analysis_dev(self, batch, grid_ptr, gs_b, gs_lat, gs_lon, coef_ptr, cs_b, cs_nm, stream=0, degree_scale=None, order_shard=None):
+        o, keep = _opts(degree_scale, order_shard, self.nmax)
+        check(lib().shb200_analysis(self._h, batch, grid_ptr, gs_b, gs_lat, gs_lon, coef_ptr, cs_b, cs_nm, stream, o))
 
-    def analysis_host(self, batch, grid_ptr, gs_b, gs_lat, gs_lon, coef_ptr, cs_b, cs_nm):
-        check(lib().shb200_analysis_host(self._h, batch, grid_ptr, gs_b, gs_lat, gs_lon, coef_ptr, cs_b, cs_nm))
+    def synthesis_host(self, batch, coef_ptr, cs_b, cs_nm, grid_ptr, gs_b, gs_lat, gs_lon, degree_scale=None):
+        o, keep = _opts(degree_scale, None, self.nmax)
+        check(lib().shb200_synthesis_host(self._h, batch, coef_ptr, cs_b, cs_nm, grid_ptr, gs_b, gs_lat, gs_lon, o))
+
+    def analysis_host(self, batch, grid_ptr, gs_b, gs_lat, gs_lon, coef_ptr, cs_b, cs_nm, degree_scale=None, order_shard=None):
+        o, keep = _opts(degree_scale, order_shard, self.nmax)
+        check(lib().shb200_analysis_host(self._h, batch, grid_ptr, gs_b, gs_lat, gs_lon, coef_ptr, cs_b, cs_nm, o))
+
+    def roundtrip_host(self, batch, coef_ptr, cs_b, cs_nm, grid_ptr, gs_b, gs_lat, gs_lon, out_ptr, os_b, os_nm,
+                       syn_scale=None, ana_scale=None):
+        o1, k1 = _opts(syn_scale, None, self.nmax)
+        o2, k2 = _opts(ana_scale, None, self.nmax)
+        check(lib().shb200_roundtrip_host(self._h, batch, coef_ptr, cs_b, cs_nm, grid_ptr, gs_b, gs_lat, gs_lon, out_ptr, os_b, os_nm, o1, o2))

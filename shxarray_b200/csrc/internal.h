@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -113,17 +114,43 @@ struct Plan {
     const int32_t* deg_of_k = nullptr;  // device [nsh] degree of each list entry
     double* dscale[2] = {nullptr, nullptr};   // device [nmax+1] per-degree scales (synthesis input / analysis output)
     bool dscale_on[2] = {false, false};
-    // staging for the *_host entry points
-    double* stage_coef = nullptr; int64_t stage_coef_elems = 0;
-    double* stage_grid = nullptr; int64_t stage_grid_elems = 0;
-    cudaStream_t own_stream = nullptr;
-    // host entry points: copy-in / copy-out streams and per-chunk events of the chunked duplex pipeline (plan.cu)
-    cudaStream_t in_stream = nullptr, out_stream = nullptr;
-    cudaEvent_t ev_in[8] = {}, ev_cmp[8] = {};
+    // device grids of shb200_multiply (multiply.cu)
+    double* mul_grid = nullptr; int64_t mul_grid_elems = 0;
     int launches_syn = 0, launches_ana = 0;
     cudaEvent_t ev[8] = {};     // SHB200_FLAG_TIMING: syn 0..3, ana 4..7
     bool timed_syn = false, timed_ana = false;
+    // ---- concurrency (plan.cu: CallScope) ----------------------------------------------------------------------------
+    // A plan is shared by every caller of the same transform (the engine caches plans; shxarray engines are process-wide
+    // singletons that dask may call from several threads).  What a call changes -- effective width, order shard, degree
+    // scale -- is applied under `mu` for the duration of the host-side launch sequence only (kernel arguments are copied at
+    // launch) and restored afterwards; the workspace (Cm, G) is handed from one stream to the next through `ev_done`.
+    std::mutex mu;
+    cudaEvent_t ev_done = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool has_last = false;
+    // names of the kernels launched by the most recent call (shb200_plan_last_kernels; tests assert the kernel family)
+    mutable std::string trace;
+    struct HostIO* hio = nullptr;   // host entry points (host_io.cu): streams, staging, events
 };
+
+inline void trace_kernel(const Plan& p, const char* name) {
+    if (!p.trace.empty()) p.trace += ',';
+    p.trace += name;
+}
+
+// What one call may change on a plan (C ABI: shb200_call_opts).
+struct CallOpts {
+    int shard_rank = 0, shard_world = 1;
+    const double* degree_scale = nullptr;   // host, nmax+1
+};
+int parse_opts(const Plan& p, const shb200_call_opts* o, CallOpts& out);
+// Device-pointer transforms without locking (the caller holds p.mu): used by the public entry points, the host entry
+// points and shb200_multiply.
+int do_synthesis(Plan& p, int batch, const double* coef, int64_t cs_b, int64_t cs_nm, double* grid, int64_t gs_b,
+                 int64_t gs_lat, int64_t gs_lon, cudaStream_t st, const CallOpts& o);
+int do_analysis(Plan& p, int batch, const double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, double* coef,
+                int64_t cs_b, int64_t cs_nm, cudaStream_t st, const CallOpts& o);
+void free_host_io(Plan& p);
 
 // number of orders m = m0, m0+mstride, ... <= nmax integrated by this plan's analysis
 inline int ana_order_count(const Plan& p) { return p.t.m0 > p.nmax ? 0 : (p.nmax - p.t.m0) / p.t.mstride + 1; }

@@ -326,6 +326,7 @@ bool launch_legendre_syn_dmma(const Plan& p, cudaStream_t st) {
         if (cudaFuncSetAttribute(dm::k_leg_syn_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm::SMEM_SYN) != cudaSuccess) return false;
     }
     dim3 grid((p.nrows + dm::TR - 1) / dm::TR, p.nmax + 1, (p.NC + dm::NCOLS - 1) / dm::NCOLS);
+    trace_kernel(p, "k_leg_syn_dmma");
     dm::k_leg_syn_dmma<<<grid, dm::NTHREADS, dm::SMEM_SYN, st>>>(p.t, p.Cm, p.G);
     return true;
 }
@@ -339,6 +340,7 @@ bool launch_legendre_ana_dmma(const Plan& p, cudaStream_t st) {
         if (cudaFuncSetAttribute(k_leg_ana_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ana::smem_bytes(ana::MAXROWS)) != cudaSuccess) return false;
     }
     dim3 grid(ana_order_count(p), (p.NC + ana::NCOLS - 1) / ana::NCOLS);
+    trace_kernel(p, "k_leg_ana_dmma");
     k_leg_ana_dmma<<<grid, ana::NTHREADS, smem, st>>>(p.t, p.G, p.Cm, rows_padded);
     return true;
 }

@@ -372,6 +372,7 @@ static bool launch_syn_tab_nwc(const Plan& p, cudaStream_t st) {
     const int nrt = (p.nrows + C_::TR - 1) / C_::TR, ntiles = nrt * (p.nmax + 1);
     const int ncolt = (p.NC + C_::NCOLS - 1) / C_::NCOLS;
     dim3 grid(std::max(1, std::min(ntiles, sms / std::min(ncolt, sms))), ncolt);
+    trace_kernel(p, NWC == 4 ? "k_leg_syn_tab<4>" : (NWC == 2 ? "k_leg_syn_tab<2>" : "k_leg_syn_tab<1>"));
     k_leg_syn_tab<NWC><<<grid, C_::NTHREADS, C_::SMEM, st>>>(p.t, p.Ptab, p.Cm, p.G, nrt, ntiles);
     return true;
 }
@@ -391,6 +392,7 @@ static bool launch_ana_tab_ncq(const Plan& p, cudaStream_t st) {
         if (cudaFuncSetAttribute(k_leg_ana_tab<NCQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_::SMEM) != cudaSuccess) return false;
     }
     dim3 grid(ana_order_count(p), (p.NC + C_::NCOLS - 1) / C_::NCOLS);
+    trace_kernel(p, NCQ == 4 ? "k_leg_ana_tab<4>" : (NCQ == 2 ? "k_leg_ana_tab<2>" : "k_leg_ana_tab<1>"));
     k_leg_ana_tab<NCQ><<<grid, C_::NTHREADS, C_::SMEM, st>>>(p.t, p.Ptab, p.G, p.Cm);
     return true;
 }

@@ -79,6 +79,7 @@ int launch_lon_syn(const Plan& p, int batch, double* grid, int64_t gs_b, int64_t
     int nl = points ? 1 : p.nlon;
     int64_t tot = (int64_t)p.nrows * nl;
     dim3 g((unsigned)((tot + 127) / 128));
+    trace_kernel(p, "k_lon_syn_dense");
     k_lon_syn_dense<<<g, 128, 0, st>>>(p.t, batch, points, p.G, grid, gs_b, gs_lat, gs_lon);
     return 0;
 }
@@ -87,6 +88,7 @@ int launch_lon_ana(const Plan& p, int batch, const double* grid, int64_t gs_b, i
     if (p.lon_fft) return launch_lon_ana_fft(p, batch, grid, gs_b, gs_lat, gs_lon, st);
     int64_t tot = (int64_t)p.nrows * (p.nmax + 1);
     dim3 g((unsigned)((tot + 127) / 128));
+    trace_kernel(p, "k_lon_ana_dense");
     k_lon_ana_dense<<<g, 128, 0, st>>>(p.t, batch, grid, gs_b, gs_lat, gs_lon, p.G);
     return 0;
 }

@@ -1,5 +1,7 @@
 // engine.multiply on the device: synthesis of both operands, pointwise product, analysis -- the
 // pattern of shtns.py:394-420 / shlib.pyx:140-152 (method="spatial") with the grids never leaving HBM.
+#include <algorithm>
+
 #include "internal.h"
 
 namespace shb {
@@ -25,27 +27,29 @@ extern "C" int shb200_multiply(shb200_plan* syn_a, shb200_plan* syn_b, shb200_pl
         return SHB200_EINVAL;
     }
     if (batch < 1 || batch > pa.maxB || batch > pb.maxB || batch > pc.maxB) { set_error("multiply: batch exceeds a plan's max_batch"); return SHB200_EINVAL; }
+    // the (up to three distinct) plans are locked in address order for the whole launch sequence
+    Plan* uniq[3] = {&pa, &pb, &pc};
+    std::sort(uniq, uniq + 3);
+    Plan** end = std::unique(uniq, uniq + 3);
+    for (Plan** q = uniq; q != end; ++q) (*q)->mu.lock();
+    struct Unlock { Plan** b; Plan** e; ~Unlock() { for (Plan** q = b; q != e; ++q) (*q)->mu.unlock(); } } unlock{uniq, end};
     SHB_CUDA(cudaSetDevice(pc.device));
     cudaStream_t st = (cudaStream_t)stream;
-    int64_t per = (int64_t)pc.nlat * pc.nlon, n = per * batch;
-    // grids live in the staging buffers of the two synthesis plans
-    auto need = [&](Plan& p) -> int {
-        if (p.stage_grid_elems >= n) return 0;
-        if (p.stage_grid) cudaFree(p.stage_grid);
-        p.stage_grid = nullptr; p.stage_grid_elems = 0;
-        SHB_CUDA(cudaMalloc((void**)&p.stage_grid, sizeof(double) * n));
-        p.stage_grid_elems = n;
-        return 0;
-    };
+    const int64_t per = (int64_t)pc.nlat * pc.nlon, n = per * batch;
+    // the two grids live in ONE buffer owned by the analysis plan (grown on demand; growing synchronises the device, so
+    // no kernel of an earlier call can still be using the old allocation)
+    if (pc.mul_grid_elems < 2 * n) {
+        if (pc.mul_grid) { SHB_CUDA(cudaDeviceSynchronize()); cudaFree(pc.mul_grid); }
+        pc.mul_grid = nullptr; pc.mul_grid_elems = 0;
+        SHB_CUDA(cudaMalloc((void**)&pc.mul_grid, sizeof(double) * 2 * n));
+        pc.mul_grid_elems = 2 * n;
+    }
+    double* ga = pc.mul_grid;
+    double* gb = pc.mul_grid + n;
+    const CallOpts none;
     int rc;
-    if ((rc = need(pa))) return rc;
-    double* gb = nullptr;
-    if (syn_a == syn_b) { SHB_CUDA(cudaMallocAsync((void**)&gb, sizeof(double) * n, st)); }
-    else { if ((rc = need(pb))) return rc; gb = pb.stage_grid; }
-    if ((rc = shb200_synthesis(syn_a, batch, coef_a, as_b, as_nm, pa.stage_grid, per, pc.nlon, 1, stream))) return rc;
-    if ((rc = shb200_synthesis(syn_b, batch, coef_b, bs_b, bs_nm, gb, per, pc.nlon, 1, stream))) return rc;
-    k_pointwise_mul<<<148 * 8, 256, 0, st>>>(pa.stage_grid, gb, n);
-    rc = shb200_analysis(ana, batch, pa.stage_grid, per, pc.nlon, 1, coef_out, os_b, os_nm, stream);
-    if (syn_a == syn_b) SHB_CUDA(cudaFreeAsync(gb, st));
-    return rc;
+    if ((rc = do_synthesis(pa, batch, coef_a, as_b, as_nm, ga, per, pc.nlon, 1, st, none))) return rc;
+    if ((rc = do_synthesis(pb, batch, coef_b, bs_b, bs_nm, gb, per, pc.nlon, 1, st, none))) return rc;
+    k_pointwise_mul<<<148 * 8, 256, 0, st>>>(ga, gb, n);
+    return do_analysis(pc, batch, ga, per, pc.nlon, 1, coef_out, os_b, os_nm, st, none);
 }

@@ -88,10 +88,11 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
     std::vector<int64_t> slot_src((size_t)T * 2, -1);
     std::vector<int64_t> dup_slot, dup_src, fwd;
     std::vector<int32_t> degk;
+    if (d.nsh < 0 || d.nsh > ((int64_t)1 << 31)) { set_error("plan_create: nsh out of range"); return SHB200_EINVAL; }
     if (d.nsh > 0) {
+        if (!d.n || !d.m) { set_error("plan_create: nsh > 0 but n/m arrays are null"); return SHB200_EINVAL; }
         fwd.assign((size_t)d.nsh, -1);
         degk.assign(d.n, d.n + d.nsh);
-        if (!d.n || !d.m) { set_error("plan_create: nsh > 0 but n/m arrays are null"); return SHB200_EINVAL; }
         p.nsh = d.nsh;
         p.full_triangle = (d.nsh == (int64_t)(N + 1) * (N + 1));
         for (int64_t k = 0; k < d.nsh; ++k) {
@@ -270,7 +271,7 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
     p.G = (double*)ptr;
     SHB_CUDA(cudaMemset(p.Cm, 0, sizeof(double) * cm_elems));
     SHB_CUDA(cudaMemset(p.G, 0, sizeof(double) * g_elems));
-    SHB_CUDA(cudaStreamCreateWithFlags(&p.own_stream, cudaStreamNonBlocking));
+    SHB_CUDA(cudaEventCreateWithFlags(&p.ev_done, cudaEventDisableTiming));
     // device-resident P_nm table for the tensor-core kernels (legendre_tab.cu) when it fits the budget
     if (p.dmma && !(d.flags & SHB200_FLAG_NO_PTABLE) && p.NC >= 32 && d.mode == SHB200_MODE_GRID) {
         p.Rpad = (R + 63) / 64 * 64;
@@ -316,34 +317,104 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
 
 static void free_plan(Plan& p) {
     cudaSetDevice(p.device);
+    free_host_io(p);
     for (void* d : p.owned) cudaFree(d);
     p.owned.clear();
-    if (p.stage_coef) cudaFree(p.stage_coef);
-    if (p.stage_grid) cudaFree(p.stage_grid);
-    if (p.own_stream) cudaStreamDestroy(p.own_stream);
-    if (p.in_stream) cudaStreamDestroy(p.in_stream);
-    if (p.out_stream) cudaStreamDestroy(p.out_stream);
-    for (int i = 0; i < 8; ++i) { if (p.ev_in[i]) cudaEventDestroy(p.ev_in[i]); if (p.ev_cmp[i]) cudaEventDestroy(p.ev_cmp[i]); }
+    if (p.mul_grid) cudaFree(p.mul_grid);
+    if (p.ev_done) cudaEventDestroy(p.ev_done);
     for (int i = 0; i < 8; ++i) if (p.ev[i]) cudaEventDestroy(p.ev[i]);
 }
 
-// A call with fewer fields than the plan was made for runs on the leading columns only: fields come in groups of 8 with
-// their cosine and sine columns adjacent, so `batch` fields occupy the first 2*ceil8(batch) columns of every Cm / G row.
-// Row strides (Cs, Gs) stay those of the plan.  Restored when the launches have been issued (one stream at a time per plan).
-struct EffectiveWidth {
+int parse_opts(const Plan& p, const shb200_call_opts* o, CallOpts& out) {
+    out = CallOpts();
+    if (!o) return 0;
+    if (o->struct_size != (int32_t)sizeof(shb200_call_opts)) { set_error("call opts: struct_size mismatch"); return SHB200_EINVAL; }
+    if (o->shard_world > 1) {
+        if (o->shard_rank < 0 || o->shard_rank >= o->shard_world) { set_error("call opts: need 0 <= shard_rank < shard_world"); return SHB200_EINVAL; }
+        out.shard_rank = o->shard_rank; out.shard_world = o->shard_world;
+    }
+    out.degree_scale = o->degree_scale;
+    (void)p;
+    return 0;
+}
+
+// Everything one call changes on the plan, applied for the duration of the host-side launch sequence (the caller holds
+// p.mu; kernel arguments are copied when a kernel is launched) and restored on exit:
+//  * effective width: a call with fewer fields than the plan was made for runs on the leading columns only -- fields come
+//    in groups of 8 with their cosine and sine columns adjacent, so `batch` fields occupy the first 2*ceil8(batch) columns
+//    of every Cm / G row; row strides (Cs, Gs) stay those of the plan;
+//  * the analysis order shard and the per-degree scale of this call (shb200_call_opts);
+//  * workspace hand-over: a call on another stream than the previous one waits for that call's last kernel.
+struct CallScope {
     Plan& p;
     int Bp0, NC0;
-    EffectiveWidth(Plan& plan, int batch) : p(plan), Bp0(plan.Bp), NC0(plan.NC) {
+    cudaStream_t st;
+    CallScope(Plan& plan, int batch, cudaStream_t stream, const CallOpts& o, int which) : p(plan), Bp0(plan.Bp), NC0(plan.NC), st(stream) {
         if (p.Bp > 8) {
             const int bp = std::min(p.Bp, (batch + 7) / 8 * 8);
             p.Bp = bp; p.NC = 2 * bp; p.t.Bp = bp; p.t.NC = 2 * bp;
         }
+        p.t.m0 = which == 1 ? o.shard_rank : 0;
+        p.t.mstride = which == 1 ? o.shard_world : 1;
+        if (p.has_last && p.last_stream != st) cudaStreamWaitEvent(st, p.ev_done, 0);
+        p.dscale_on[0] = p.dscale_on[1] = false;
+        if (o.degree_scale) {
+            // pageable source: the runtime stages the nmax+1 values before returning, so the caller's array is free again
+            cudaMemcpyAsync(p.dscale[which], o.degree_scale, sizeof(double) * (p.nmax + 1), cudaMemcpyHostToDevice, st);
+            p.dscale_on[which] = true;
+        }
+        p.trace.clear();
     }
-    ~EffectiveWidth() { p.Bp = Bp0; p.NC = NC0; p.t.Bp = Bp0; p.t.NC = NC0; }
+    ~CallScope() {
+        cudaEventRecord(p.ev_done, st);
+        p.last_stream = st; p.has_last = true;
+        p.Bp = Bp0; p.NC = NC0; p.t.Bp = Bp0; p.t.NC = NC0;
+        p.t.m0 = 0; p.t.mstride = 1;
+        p.dscale_on[0] = p.dscale_on[1] = false;
+    }
 };
 
 static int check_batch(const Plan& p, int batch) {
     if (batch < 1 || batch > p.maxB) { set_error("batch must be in [1, max_batch] of the plan"); return SHB200_EINVAL; }
+    return 0;
+}
+
+int do_synthesis(Plan& p, int batch, const double* coef, int64_t cs_b, int64_t cs_nm, double* grid, int64_t gs_b,
+                 int64_t gs_lat, int64_t gs_lon, cudaStream_t st, const CallOpts& o) {
+    int rc = check_batch(p, batch);
+    if (rc) return rc;
+    SHB_CUDA(cudaSetDevice(p.device));
+    const bool tm = p.flags & SHB200_FLAG_TIMING;
+    CallScope scope(p, batch, st, o, 0);
+    if (tm) cudaEventRecord(p.ev[0], st);
+    launch_pack(p, batch, coef, cs_b, cs_nm, st);
+    if (tm) cudaEventRecord(p.ev[1], st);
+    launch_legendre_syn(p, st);
+    if (tm) cudaEventRecord(p.ev[2], st);
+    rc = launch_lon_syn(p, batch, grid, gs_b, gs_lat, gs_lon, st);
+    if (rc) return rc;
+    if (tm) { cudaEventRecord(p.ev[3], st); p.timed_syn = true; }
+    SHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int do_analysis(Plan& p, int batch, const double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, double* coef,
+                int64_t cs_b, int64_t cs_nm, cudaStream_t st, const CallOpts& o) {
+    if (p.quadrature == SHB200_QUAD_NONE) { set_error("analysis: plan was created without quadrature weights"); return SHB200_EINVAL; }
+    int rc = check_batch(p, batch);
+    if (rc) return rc;
+    SHB_CUDA(cudaSetDevice(p.device));
+    const bool tm = p.flags & SHB200_FLAG_TIMING;
+    CallScope scope(p, batch, st, o, 1);
+    if (tm) cudaEventRecord(p.ev[4], st);
+    rc = launch_lon_ana(p, batch, grid, gs_b, gs_lat, gs_lon, st);
+    if (rc) return rc;
+    if (tm) cudaEventRecord(p.ev[5], st);
+    launch_legendre_ana(p, st);
+    if (tm) cudaEventRecord(p.ev[6], st);
+    launch_unpack(p, batch, coef, cs_b, cs_nm, st);
+    if (tm) { cudaEventRecord(p.ev[7], st); p.timed_ana = true; }
+    SHB_CUDA(cudaGetLastError());
     return 0;
 }
 
@@ -387,72 +458,42 @@ int shb200_plan_get_info(const shb200_plan* plan, shb200_plan_info* info) {
 }
 
 int shb200_synthesis(shb200_plan* plan, int32_t batch, const double* coef, int64_t cs_b, int64_t cs_nm,
-                     double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, void* stream) {
+                     double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, void* stream, const shb200_call_opts* opts) {
     if (!plan || !coef || !grid) { set_error("synthesis: null argument"); return SHB200_EINVAL; }
     Plan& p = plan->p;
-    int rc = check_batch(p, batch);
+    CallOpts o;
+    int rc = parse_opts(p, opts, o);
     if (rc) return rc;
-    SHB_CUDA(cudaSetDevice(p.device));
-    cudaStream_t st = (cudaStream_t)stream;
-    const bool tm = p.flags & SHB200_FLAG_TIMING;
-    EffectiveWidth width(p, batch);
-    if (tm) cudaEventRecord(p.ev[0], st);
-    launch_pack(p, batch, coef, cs_b, cs_nm, st);
-    if (tm) cudaEventRecord(p.ev[1], st);
-    launch_legendre_syn(p, st);
-    if (tm) cudaEventRecord(p.ev[2], st);
-    rc = launch_lon_syn(p, batch, grid, gs_b, gs_lat, gs_lon, st);
-    if (rc) return rc;
-    if (tm) { cudaEventRecord(p.ev[3], st); p.timed_syn = true; }
-    SHB_CUDA(cudaGetLastError());
-    return 0;
+    std::lock_guard<std::mutex> lock(p.mu);
+    return do_synthesis(p, batch, coef, cs_b, cs_nm, grid, gs_b, gs_lat, gs_lon, (cudaStream_t)stream, o);
 }
 
 int shb200_analysis(shb200_plan* plan, int32_t batch, const double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon,
-                    double* coef, int64_t cs_b, int64_t cs_nm, void* stream) {
+                    double* coef, int64_t cs_b, int64_t cs_nm, void* stream, const shb200_call_opts* opts) {
     if (!plan || !coef || !grid) { set_error("analysis: null argument"); return SHB200_EINVAL; }
     Plan& p = plan->p;
-    if (p.quadrature == SHB200_QUAD_NONE) { set_error("analysis: plan was created without quadrature weights"); return SHB200_EINVAL; }
-    int rc = check_batch(p, batch);
+    CallOpts o;
+    int rc = parse_opts(p, opts, o);
     if (rc) return rc;
-    SHB_CUDA(cudaSetDevice(p.device));
-    cudaStream_t st = (cudaStream_t)stream;
-    const bool tm = p.flags & SHB200_FLAG_TIMING;
-    EffectiveWidth width(p, batch);
-    if (tm) cudaEventRecord(p.ev[4], st);
-    rc = launch_lon_ana(p, batch, grid, gs_b, gs_lat, gs_lon, st);
-    if (rc) return rc;
-    if (tm) cudaEventRecord(p.ev[5], st);
-    launch_legendre_ana(p, st);
-    if (tm) cudaEventRecord(p.ev[6], st);
-    launch_unpack(p, batch, coef, cs_b, cs_nm, st);
-    if (tm) { cudaEventRecord(p.ev[7], st); p.timed_ana = true; }
-    SHB_CUDA(cudaGetLastError());
-    return 0;
+    std::lock_guard<std::mutex> lock(p.mu);
+    return do_analysis(p, batch, grid, gs_b, gs_lat, gs_lon, coef, cs_b, cs_nm, (cudaStream_t)stream, o);
 }
 
-int shb200_plan_set_degree_scale(shb200_plan* plan, int32_t which, const double* scale, int32_t n) {
-    if (!plan || which < 0 || which > 1) { set_error("set_degree_scale: bad plan or selector"); return SHB200_EINVAL; }
-    Plan& p = plan->p;
-    if (!scale) { p.dscale_on[which] = false; return 0; }
-    if (n != p.nmax + 1) { set_error("set_degree_scale: need nmax+1 values"); return SHB200_EINVAL; }
-    SHB_CUDA(cudaSetDevice(p.device));
-    SHB_CUDA(cudaMemcpy(p.dscale[which], scale, sizeof(double) * n, cudaMemcpyHostToDevice));
-    p.dscale_on[which] = true;
-    return 0;
-}
-
-int shb200_plan_set_order_shard(shb200_plan* plan, int32_t rank, int32_t world) {
-    if (!plan || world < 1 || rank < 0 || rank >= world) { set_error("set_order_shard: need 0 <= rank < world"); return SHB200_EINVAL; }
-    plan->p.t.m0 = rank;
-    plan->p.t.mstride = world;
-    return 0;
+int shb200_plan_last_kernels(const shb200_plan* plan, char* buf, int32_t n) {
+    if (!plan || !buf || n < 1) { set_error("plan_last_kernels: invalid argument"); return SHB200_EINVAL; }
+    Plan& p = const_cast<Plan&>(plan->p);
+    std::lock_guard<std::mutex> lock(p.mu);
+    const size_t len = std::min(p.trace.size(), (size_t)n - 1);
+    memcpy(buf, p.trace.data(), len);
+    buf[len] = 0;
+    return (int)p.trace.size();
 }
 
 int shb200_plan_stage_times(shb200_plan* plan, double* ms, int32_t n) {
     if (!plan || !ms || n < 6) { set_error("plan_stage_times: need a plan and room for 6 values"); return SHB200_EINVAL; }
     Plan& p = plan->p;
     if (!(p.flags & SHB200_FLAG_TIMING)) { set_error("plan_stage_times: plan was created without SHB200_FLAG_TIMING"); return SHB200_EINVAL; }
+    std::lock_guard<std::mutex> lock(p.mu);
     SHB_CUDA(cudaSetDevice(p.device));
     for (int i = 0; i < 6; ++i) ms[i] = 0.0;
     float f;
@@ -465,127 +506,6 @@ int shb200_plan_stage_times(shb200_plan* plan, double* ms, int32_t n) {
         for (int i = 0; i < 3; ++i) { SHB_CUDA(cudaEventElapsedTime(&f, p.ev[4 + i], p.ev[5 + i])); ms[3 + i] = f; }
     }
     return 0;
-}
-
-// extent (in elements) spanned by a strided 2-D / 3-D array
-static int64_t span2(int64_t n0, int64_t s0, int64_t n1, int64_t s1) { return (n0 - 1) * llabs(s0) + (n1 - 1) * llabs(s1) + 1; }
-
-static int ensure_stage(double** buf, int64_t* have, int64_t need) {
-    if (*have >= need) return 0;
-    if (*buf) cudaFree(*buf);
-    *buf = nullptr; *have = 0;
-    SHB_CUDA(cudaMalloc((void**)buf, sizeof(double) * need));
-    *have = need;
-    return 0;
-}
-
-// ---- host-buffer entry points ---------------------------------------------------------------------
-// The transforms are PCIe-bound here (cfg3: 0.27 + 0.57 GB per direction against ~3 ms of kernels), so the batch is cut into
-// up to 4 chunks of whole fields that flow through three streams: copy-in (H2D) -> kernels -> copy-out (D2H).  Both copy
-// directions then run at once (the link is full duplex) and the kernels hide behind them: time per call ~ the larger of the
-// two transfers instead of their sum plus the kernels.  Needs the batch axis to be the slowest of both host arrays (chunks
-// are then contiguous spans); anything else takes the single-shot path.
-static int host_chunks(int batch) { return batch >= 32 ? 4 : (batch >= 16 ? 2 : 1); }
-
-static int ensure_pipeline(Plan& p) {
-    if (p.in_stream) return 0;
-    SHB_CUDA(cudaStreamCreateWithFlags(&p.in_stream, cudaStreamNonBlocking));
-    SHB_CUDA(cudaStreamCreateWithFlags(&p.out_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 8; ++i) {
-        SHB_CUDA(cudaEventCreateWithFlags(&p.ev_in[i], cudaEventDisableTiming));
-        SHB_CUDA(cudaEventCreateWithFlags(&p.ev_cmp[i], cudaEventDisableTiming));
-    }
-    return 0;
-}
-
-int shb200_synthesis_host(shb200_plan* plan, int32_t batch, const double* coef, int64_t cs_b, int64_t cs_nm,
-                          double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon) {
-    if (!plan || !coef || !grid) { set_error("synthesis_host: null argument"); return SHB200_EINVAL; }
-    Plan& p = plan->p;
-    int rc = check_batch(p, batch);
-    if (rc) return rc;
-    if (cs_b < 0 || cs_nm < 0 || gs_b < 0 || gs_lat < 0 || gs_lon < 0) { set_error("host entry points need non-negative strides"); return SHB200_EINVAL; }
-    SHB_CUDA(cudaSetDevice(p.device));
-    int64_t ncoef = span2(batch, cs_b, p.nsh, cs_nm);
-    bool points = p.mode == SHB200_MODE_POINTS;
-    auto grid_span = [&](int64_t nb) { return points ? span2(nb, gs_b, p.nlat, gs_lat) : span2(nb, gs_b, p.nlat, gs_lat) + (p.nlon - 1) * gs_lon; };
-    int64_t ngrid = grid_span(batch);
-    if ((rc = ensure_stage(&p.stage_coef, &p.stage_coef_elems, ncoef))) return rc;
-    if ((rc = ensure_stage(&p.stage_grid, &p.stage_grid_elems, ngrid))) return rc;
-    const int nchunk = host_chunks(batch);
-    const bool sliceable = cs_b >= span2(1, 0, p.nsh, cs_nm) && gs_b >= grid_span(1);
-    if (nchunk == 1 || !sliceable) {
-        SHB_CUDA(cudaMemcpyAsync(p.stage_coef, coef, sizeof(double) * ncoef, cudaMemcpyHostToDevice, p.own_stream));
-        rc = shb200_synthesis(plan, batch, p.stage_coef, cs_b, cs_nm, p.stage_grid, gs_b, gs_lat, gs_lon, p.own_stream);
-        if (rc) return rc;
-        SHB_CUDA(cudaMemcpyAsync(grid, p.stage_grid, sizeof(double) * ngrid, cudaMemcpyDeviceToHost, p.own_stream));
-        SHB_CUDA(cudaStreamSynchronize(p.own_stream));
-        return 0;
-    }
-    if ((rc = ensure_pipeline(p))) return rc;
-    const int per = ((batch + nchunk - 1) / nchunk + 7) / 8 * 8;         // whole groups of 8 fields per chunk
-    int c = 0;
-    for (int b0 = 0; b0 < batch; b0 += per, ++c) {
-        const int nb = std::min(per, batch - b0);
-        const int64_t co = (int64_t)b0 * cs_b, go = (int64_t)b0 * gs_b;
-        SHB_CUDA(cudaMemcpyAsync(p.stage_coef + co, coef + co, sizeof(double) * span2(nb, cs_b, p.nsh, cs_nm), cudaMemcpyHostToDevice, p.in_stream));
-        SHB_CUDA(cudaEventRecord(p.ev_in[c], p.in_stream));
-        SHB_CUDA(cudaStreamWaitEvent(p.own_stream, p.ev_in[c], 0));
-        rc = shb200_synthesis(plan, nb, p.stage_coef + co, cs_b, cs_nm, p.stage_grid + go, gs_b, gs_lat, gs_lon, p.own_stream);
-        if (rc) break;
-        SHB_CUDA(cudaEventRecord(p.ev_cmp[c], p.own_stream));
-        SHB_CUDA(cudaStreamWaitEvent(p.out_stream, p.ev_cmp[c], 0));
-        SHB_CUDA(cudaMemcpyAsync(grid + go, p.stage_grid + go, sizeof(double) * grid_span(nb), cudaMemcpyDeviceToHost, p.out_stream));
-    }
-    cudaStreamSynchronize(p.in_stream);
-    cudaStreamSynchronize(p.own_stream);
-    SHB_CUDA(cudaStreamSynchronize(p.out_stream));
-    return rc;
-}
-
-int shb200_analysis_host(shb200_plan* plan, int32_t batch, const double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon,
-                         double* coef, int64_t cs_b, int64_t cs_nm) {
-    if (!plan || !coef || !grid) { set_error("analysis_host: null argument"); return SHB200_EINVAL; }
-    Plan& p = plan->p;
-    int rc = check_batch(p, batch);
-    if (rc) return rc;
-    if (cs_b < 0 || cs_nm < 0 || gs_b < 0 || gs_lat < 0 || gs_lon < 0) { set_error("host entry points need non-negative strides"); return SHB200_EINVAL; }
-    SHB_CUDA(cudaSetDevice(p.device));
-    int64_t nfull = (int64_t)(p.nmax + 1) * (p.nmax + 1);
-    int64_t ncoef = span2(batch, cs_b, nfull, cs_nm);
-    auto grid_span = [&](int64_t nb) { return span2(nb, gs_b, p.nlat, gs_lat) + (p.nlon - 1) * gs_lon; };
-    int64_t ngrid = grid_span(batch);
-    if ((rc = ensure_stage(&p.stage_coef, &p.stage_coef_elems, ncoef))) return rc;
-    if ((rc = ensure_stage(&p.stage_grid, &p.stage_grid_elems, ngrid))) return rc;
-    const int nchunk = host_chunks(batch);
-    const bool sliceable = cs_b >= span2(1, 0, nfull, cs_nm) && gs_b >= grid_span(1);
-    if (nchunk == 1 || !sliceable) {
-        SHB_CUDA(cudaMemcpyAsync(p.stage_grid, grid, sizeof(double) * ngrid, cudaMemcpyHostToDevice, p.own_stream));
-        rc = shb200_analysis(plan, batch, p.stage_grid, gs_b, gs_lat, gs_lon, p.stage_coef, cs_b, cs_nm, p.own_stream);
-        if (rc) return rc;
-        SHB_CUDA(cudaMemcpyAsync(coef, p.stage_coef, sizeof(double) * ncoef, cudaMemcpyDeviceToHost, p.own_stream));
-        SHB_CUDA(cudaStreamSynchronize(p.own_stream));
-        return 0;
-    }
-    if ((rc = ensure_pipeline(p))) return rc;
-    const int per = ((batch + nchunk - 1) / nchunk + 7) / 8 * 8;
-    int c = 0;
-    for (int b0 = 0; b0 < batch; b0 += per, ++c) {
-        const int nb = std::min(per, batch - b0);
-        const int64_t co = (int64_t)b0 * cs_b, go = (int64_t)b0 * gs_b;
-        SHB_CUDA(cudaMemcpyAsync(p.stage_grid + go, grid + go, sizeof(double) * grid_span(nb), cudaMemcpyHostToDevice, p.in_stream));
-        SHB_CUDA(cudaEventRecord(p.ev_in[c], p.in_stream));
-        SHB_CUDA(cudaStreamWaitEvent(p.own_stream, p.ev_in[c], 0));
-        rc = shb200_analysis(plan, nb, p.stage_grid + go, gs_b, gs_lat, gs_lon, p.stage_coef + co, cs_b, cs_nm, p.own_stream);
-        if (rc) break;
-        SHB_CUDA(cudaEventRecord(p.ev_cmp[c], p.own_stream));
-        SHB_CUDA(cudaStreamWaitEvent(p.out_stream, p.ev_cmp[c], 0));
-        SHB_CUDA(cudaMemcpyAsync(coef + co, p.stage_coef + co, sizeof(double) * span2(nb, cs_b, nfull, cs_nm), cudaMemcpyDeviceToHost, p.out_stream));
-    }
-    cudaStreamSynchronize(p.in_stream);
-    cudaStreamSynchronize(p.own_stream);
-    SHB_CUDA(cudaStreamSynchronize(p.out_stream));
-    return rc;
 }
 
 // Gauss-Legendre nodes/weights by Newton iteration on P_n in long double.

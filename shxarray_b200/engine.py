@@ -144,23 +144,27 @@ _w64 = {}
 
 
 def _weights64(n):
+    """three sequences of odd 64-bit position weights (golden-ratio, sqrt(2) and sqrt(3) multipliers)"""
     if n not in _w64:
         if len(_w64) > 16:
             _w64.clear()
-        _w64[n] = (np.arange(n, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)) | np.uint64(1)
+        i = np.arange(1, n + 1, dtype=np.uint64)
+        _w64[n] = tuple((i * np.uint64(c)) | np.uint64(1) for c in (0x9E3779B97F4A7C15, 0x6A09E667F3BCC909, 0xBB67AE8584CAA73B))
     return _w64[n]
 
 
 def _digest(*arrays):
     """Plan-cache key of coordinate / index arrays.  Small arrays: blake2b of the bytes.  Large ones (the nm list of a
-    high-degree field is megabytes): two position-weighted 64-bit checksums, ~1 ms instead of ~15 ms per call."""
+    high-degree field is megabytes): length, the plain sum, three position-weighted 64-bit checksums with unrelated weight
+    sequences and the first / last 64 elements -- ~1.5 ms instead of ~15 ms per call; an accidental collision needs four
+    independent 64-bit sums to agree."""
     h = hashlib.blake2b(digest_size=16)
     for a in arrays:
         if a is None:
             h.update(b"-")
             continue
         a = np.ascontiguousarray(a)
-        h.update(str(a.dtype).encode() + str(a.shape).encode())
+        h.update(str(a.dtype).encode() + str(a.shape).encode() + str(a.nbytes).encode())
         if a.nbytes <= 65536:
             h.update(a.tobytes())
         else:
@@ -168,8 +172,10 @@ def _digest(*arrays):
             n8 = raw.size // 8 * 8
             h.update(raw[n8:].tobytes())
             v = raw[:n8].view(np.uint64)
-            w = _weights64(len(v))
-            h.update(int(np.add.reduce(v)).to_bytes(8, "little") + int(np.add.reduce(v * w)).to_bytes(8, "little"))
+            with np.errstate(over="ignore"):
+                h.update(int(np.add.reduce(v)).to_bytes(8, "little"))
+                for w in _weights64(len(v)):
+                    h.update(int(np.add.reduce(v * w)).to_bytes(8, "little"))
             h.update(a.reshape(-1)[:64].tobytes() + a.reshape(-1)[-64:].tobytes())
     return h.hexdigest()
 
@@ -233,14 +239,16 @@ class SHEngine:
                     if getattr(p2, "_gkey", None) == gkey and p2.max_batch >= maxb:
                         self._plans.move_to_end(k2)
                         return p2
+            # Replaced, superseded and evicted plans are only DROPPED from the cache: another thread (or the caller, in
+            # multiply) may still be inside a call on them.  capi.Plan.__del__ destroys a plan with its last reference.
             if plan is not None:
                 del self._plans[key]
-                plan.close()
             if quadrature != capi.QUAD_NONE:
                 # the new plan supersedes synthesis-only plans of the same grid that are not larger
                 for k2 in [k2 for k2, p2 in self._plans.items()
                            if k2[2] == capi.QUAD_NONE and getattr(p2, "_gkey", None) == gkey and p2.max_batch <= maxb]:
-                    self._plans.pop(k2).close()
+                    del self._plans[k2]
+            del plan
             plan = capi.Plan(nmax, lat, lon, max_batch=maxb, n=n, m=m, mode=mode, quadrature=quadrature,
                              weight=weight, lat_weights=lat_weights, flags=flags, device=self.device)
             plan._gkey = gkey
@@ -250,14 +258,25 @@ class SHEngine:
             while len(self._plans) > 3 and (len(self._plans) > self.MAX_PLANS or total > self.CACHE_BUDGET):   # multiply() holds 3 plans
                 _, old = self._plans.popitem(last=False)
                 total -= int(old.info.workspace_bytes)
-                old.close()
+                del old
             return plan
 
     def clear(self):
         with self._lock:
-            for p in self._plans.values():
-                p.close()
             self._plans.clear()
+
+    #: numpy results up to this size are handed out of the library's page-locked pool (capi.pinned_empty): the device
+    #: writes them by DMA, no bounce copy, no first-touch page faults, and a later analysis of that array uploads by DMA too
+    PINNED_OUT_MAX = 8 << 30
+
+    def _host_empty(self, shape):
+        n = int(np.prod(shape, dtype=np.int64)) * 8
+        if 0 < n <= self.PINNED_OUT_MAX:
+            try:
+                return capi.pinned_empty(shape)
+            except capi.SHB200Error:
+                pass
+        return np.empty(shape, dtype=np.float64)
 
     # ------------------------------------------------------------------------------------------
     def synthesis(self, coef, n=None, m=None, lon=None, lat=None, nmax=None, points=False, nm_axis=-1,
@@ -309,7 +328,6 @@ class SHEngine:
         if points and len(lon) != len(lat):
             raise ValueError("point synthesis needs equally sized lon and lat")
         plan = self.get_plan(nmax, lat, lon, B, n=n, m=m, mode=mode, flags=flags)
-        plan.set_degree_scale(0, degree_scale)
         L, K = len(lat), len(lon)
         if points:
             shape = (B, L) if layout == "batch_first" else (L, B)
@@ -324,7 +342,11 @@ class SHEngine:
             stream = torch.cuda.current_stream(coef.device).cuda_stream
         else:
             if out is None:
-                out = np.empty(shape, dtype=np.float64)
+                out = self._host_empty(shape)
+            elif min(out.strides) < 0:
+                raise ValueError("out= views with negative strides are not supported")
+            if min(coef.strides) < 0:
+                coef = np.ascontiguousarray(coef)
             es = lambda a: [s // 8 for s in a.strides]
             ptr = lambda a: a.ctypes.data
             stream = None
@@ -340,9 +362,9 @@ class SHEngine:
             cptr = ptr(coef) + 8 * b0 * cs[0]
             gptr = ptr(out) + 8 * b0 * gs_b
             if tor:
-                plan.synthesis_dev(nb, cptr, cs[0], cs[1], gptr, gs_b, gs_lat, gs_lon, stream)
+                plan.synthesis_dev(nb, cptr, cs[0], cs[1], gptr, gs_b, gs_lat, gs_lon, stream, degree_scale=degree_scale)
             else:
-                plan.synthesis_host(nb, cptr, cs[0], cs[1], gptr, gs_b, gs_lat, gs_lon)
+                plan.synthesis_host(nb, cptr, cs[0], cs[1], gptr, gs_b, gs_lat, gs_lon, degree_scale=degree_scale)
             self.launches += plan.info.launches_synthesis
         if squeeze:
             out = out[0] if layout == "batch_first" else out[..., 0]
@@ -391,8 +413,6 @@ class SHEngine:
         else:
             raise ValueError("quadrature must be 'shlib', 'gauss' or 'weights'")
         plan = self.get_plan(nmax, lat, lon, B, quadrature=q, weight=wgt, lat_weights=lw, flags=flags)
-        plan.set_degree_scale(1, degree_scale)
-        plan.set_order_shard(*(order_shard if order_shard is not None else (0, 1)))   # (rank, world): m-sharded analysis
         nsh = (nmax + 1) ** 2
         if tor:
             import torch
@@ -403,7 +423,9 @@ class SHEngine:
             stream = torch.cuda.current_stream(grid.device).cuda_stream
         else:
             if out is None:
-                out = np.empty((B, nsh), dtype=np.float64)
+                out = self._host_empty((B, nsh))
+            elif min(out.strides) < 0:
+                raise ValueError("out= views with negative strides are not supported")
             es = lambda a: [s // 8 for s in a.strides]
             ptr = lambda a: a.ctypes.data
             stream = None
@@ -420,14 +442,52 @@ class SHEngine:
             gptr = ptr(grid) + 8 * b0 * gs_b
             cptr = ptr(out) + 8 * b0 * cs[0]
             if tor:
-                plan.analysis_dev(nb, gptr, gs_b, gs_lat, gs_lon, cptr, cs[0], cs[1], stream)
+                plan.analysis_dev(nb, gptr, gs_b, gs_lat, gs_lon, cptr, cs[0], cs[1], stream, degree_scale=degree_scale, order_shard=order_shard)
             else:
-                plan.analysis_host(nb, gptr, gs_b, gs_lat, gs_lon, cptr, cs[0], cs[1])
+                plan.analysis_host(nb, gptr, gs_b, gs_lat, gs_lon, cptr, cs[0], cs[1], degree_scale=degree_scale, order_shard=order_shard)
             self.launches += plan.info.launches_analysis
         if squeeze:
             out = out[0]
         return out
 
+
+    # ------------------------------------------------------------------------------------------
+    def roundtrip(self, coef, nmax, lon, lat, quadrature="gauss", lat_weights=None, weight=None, grid_out=None, out=None):
+        """Synthesis to the grid AND analysis of that grid in one pipelined call on host arrays (shb200_roundtrip_host):
+        returns (grid [B, nlat, nlon], coef_out [B, (nmax+1)^2]).  Same results and same bytes over PCIe as
+        ``g = synthesis(coef); c = analysis(g)`` -- the analysis input is read back from the host grid -- but the grid of
+        chunk k+1 is downloaded while the grid of chunk k is uploaded.  coef: numpy [B, (nmax+1)^2], full triangle."""
+        lon = np.ascontiguousarray(lon, dtype=np.float64)
+        lat = np.ascontiguousarray(lat, dtype=np.float64)
+        coef = np.asarray(coef, dtype=np.float64)
+        if coef.ndim != 2 or coef.shape[1] != (nmax + 1) ** 2:
+            raise ValueError("coef must be [B, (nmax+1)^2]")
+        if min(coef.strides) < 0:
+            coef = np.ascontiguousarray(coef)
+        B, L, K = coef.shape[0], len(lat), len(lon)
+        if quadrature == "shlib":
+            q, wgt, lw = capi.QUAD_SHLIB, analysis_weight_shlib(lon, lat), None
+        elif quadrature == "gauss":
+            q, wgt, lw = capi.QUAD_LATWEIGHTS, 1.0 / (2.0 * K), gauss_lat_weights(lat)
+        elif quadrature == "weights":
+            q, wgt, lw = capi.QUAD_LATWEIGHTS, (1.0 if weight is None else float(weight)), np.asarray(lat_weights, dtype=np.float64)
+        else:
+            raise ValueError("quadrature must be 'shlib', 'gauss' or 'weights'")
+        plan = self.get_plan(nmax, lat, lon, B, quadrature=q, weight=wgt, lat_weights=lw)
+        if grid_out is None:
+            grid_out = capi.pinned_empty((B, L, K))
+        if out is None:
+            out = self._host_empty((B, (nmax + 1) ** 2))
+        gs = [s // 8 for s in grid_out.strides]
+        cs = [s // 8 for s in coef.strides]
+        os_ = [s // 8 for s in out.strides]
+        step = plan.max_batch
+        for b0 in range(0, B, step):
+            nb = min(step, B - b0)
+            plan.roundtrip_host(nb, coef.ctypes.data + 8 * b0 * cs[0], cs[0], cs[1], grid_out.ctypes.data + 8 * b0 * gs[0], gs[0], gs[1], gs[2],
+                                out.ctypes.data + 8 * b0 * os_[0], os_[0], os_[1])
+            self.launches += plan.info.launches_synthesis + plan.info.launches_analysis
+        return grid_out, out
 
     # ------------------------------------------------------------------------------------------
     def multiply(self, coef_a, nmax_a, coef_b, nmax_b):
@@ -447,9 +507,10 @@ class SHEngine:
         B = ta.shape[0]
         na, ma = _nm_index_cached(int(nmax_a), 0)
         nb_, mb = _nm_index_cached(int(nmax_b), 0)
+        # the analysis plan first: a synthesis operand of the same degree (nmax_a or nmax_b = 0) then shares it
+        pc = self.get_plan(nmax, lat, lon, B, quadrature=capi.QUAD_LATWEIGHTS, weight=1.0 / (2.0 * len(lon)), lat_weights=lw)
         pa = self.get_plan(int(nmax_a), lat, lon, B, n=na, m=ma)
         pb = pa if nmax_a == nmax_b else self.get_plan(int(nmax_b), lat, lon, B, n=nb_, m=mb)
-        pc = self.get_plan(nmax, lat, lon, B, quadrature=capi.QUAD_LATWEIGHTS, weight=1.0 / (2.0 * len(lon)), lat_weights=lw)
         out = torch.empty((B, (nmax + 1) ** 2), dtype=torch.float64, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
         step = min(pa.max_batch, pb.max_batch, pc.max_batch)

@@ -6,7 +6,13 @@ core/shcomputebase.py:1-20; loader core/shxarbase.py:240-259) as a sibling of ``
 (src/builtin_backend/shlib.pyx:24-159) and ``engine='shtns'`` (src/shtns_backend/shtns.py:287-420).
 Same method names, argument meaning and error behaviour; the accessor calls
 ``da.sh.synthesis(engine='b200')``, ``da.sh.analysis(nmax, engine='b200')``,
-``da.sh.multiply(other, engine='b200')`` and everything layered on them work unchanged.
+``da.sh.multiply(other, engine='b200')`` and everything layered on those three calls work unchanged.  The shlib-only
+extras (gaunt, gauntReal, wigner3j, p2s: shlib.pyx:49-60) raise the base class's "not implemented" RuntimeError
+(shcomputebase.py:19-20) -- the accessor defaults to engine="shlib" for them.  Unknown keyword arguments raise TypeError.
+
+Known deliberate difference from shlib (shlib.pyx:101-108): ``lonlat_grid(lon=, lat=, gtype="point")``
+returns a true point set (lon/lat sharing the dimension ``nlonlat``) -- shlib overwrites it with a grid dataset, so
+equal-length lon/lat always give a grid there; here, as with engine='shtns' (shtns.py:355-363), they give points.
 
 This module needs xarray + shxarray at import time (it is only imported through the entry point or
 explicitly); everything below it (``engine.SHEngine``, ``capi``) works with numpy/torch alone.
@@ -93,6 +99,7 @@ class B200Backend(SHComputeBackendBase):
         dast = dast.transpose(auxdim, "nm")
         coef = np.asarray(dast.data, dtype=np.float64)           # [B, nsh], any strides
         # degree_scale=<nmax+1 factors or an IsoKernelBase> fuses an isotropic kernel into the transform
+        _reject_unknown(kwargs, ("degree_scale",))
         ds = kwargs.get("degree_scale", None)
         if ds is not None and hasattr(ds, "_dsiso"):
             ds = np.asarray(ds._dsiso.sel(n=np.arange(int(n.max()) + 1)).data, dtype=np.float64)
@@ -138,6 +145,7 @@ class B200Backend(SHComputeBackendBase):
         grid = np.asarray(dast.data, dtype=np.float64)
         lon = np.asarray(loninfo.var.data, dtype=np.float64)
         lat = np.asarray(latinfo.var.data, dtype=np.float64)
+        _reject_unknown(kwargs, ("degree_scale",))
         ds = kwargs.get("degree_scale", None)
         if ds is not None and hasattr(ds, "_dsiso"):
             ds = np.asarray(ds._dsiso.sel(n=np.arange(int(nmax) + 1)).data, dtype=np.float64)
@@ -152,17 +160,67 @@ class B200Backend(SHComputeBackendBase):
         return daout
 
     # ------------------------------------------------------------------------------------------
-    def multiply(self, dash1, dash2, **kwargs):
-        """Product of two SH fields through the spatial domain (shtns.py:394-420): Gauss grid of nmax1+nmax2,
-        two syntheses, pointwise product, Gauss-quadrature analysis."""
-        nmax = dash1.sh.nmax + dash2.sh.nmax
-        dslonlat = self.lonlat_grid(nmax=nmax, gtype="gauss")
-        dagrd1 = self.synthesis(dash1, dslonlat)
-        dagrd2 = self.synthesis(dash2, dslonlat)
-        dagrd = dagrd1 * dagrd2
-        dagrd.lon.attrs["shxarray_gtype"] = "gauss"
-        dagrd.lat.attrs["shxarray_gtype"] = "gauss"
-        return self.analysis(dagrd, nmax=nmax, quadrature="gauss")
+    def multiply(self, dash1, dash2, method="spatial", **kwargs):
+        """Product of two SH fields through the spatial domain (shtns.py:394-420; shlib.pyx:140-152 method="spatial"): Gauss
+        grid of nmax1+nmax2, two syntheses, pointwise product, Gauss-quadrature analysis -- all four steps on the device
+        (shb200_multiply), only the coefficients cross PCIe.  method="spectral" (Gaunt coefficients, shlib.pyx:130-139) is
+        the shlib engine's own algorithm and is not provided here."""
+        if method != "spatial":
+            self._notImplemented(f"multiply(method={method!r})")
+        _reject_unknown(kwargs, ())
+        nmax1, nmax2 = int(dash1.sh.nmax), int(dash2.sh.nmax)
+        nmax = nmax1 + nmax2
+        name = dash1.name
+
+        def full_triangle(da, nm_max):
+            """[B, (nmax+1)^2] in standard nm order (missing coefficients = 0, e.g. nmin > 0), aux dims stacked"""
+            dast, auxdim = _stack_aux(da, ["nm"])
+            dast = dast.transpose(auxdim, "nm")
+            n = dast.nm.n.data.astype(np.int64)
+            m = dast.nm.m.data.astype(np.int64)
+            full = np.zeros((dast.sizes[auxdim], (nm_max + 1) ** 2))
+            full[:, n * n + n + m] = np.asarray(dast.data, dtype=np.float64)
+            return full, dast, auxdim
+
+        a, dast1, aux1 = full_triangle(dash1, nmax1)
+        b, dast2, aux2 = full_triangle(dash2, nmax2)
+        # broadcasting over the auxiliary dimension like the reference's grid product: equal batch sizes or a single field
+        if a.shape[0] != b.shape[0]:
+            if a.shape[0] == 1:
+                a = np.repeat(a, b.shape[0], axis=0)
+                dast1, aux1 = dast2, aux2
+            elif b.shape[0] == 1:
+                b = np.repeat(b, a.shape[0], axis=0)
+            else:
+                raise RuntimeError("multiply: auxiliary dimensions of the two inputs do not match")
+        out = self._engine.multiply(a, nmax1, b, nmax2)
+        coords = {aux1: dast1.coords[aux1], SHindexBase.name: SHindexBase.nm_mi(nmax, 0)}
+        daout = xr.DataArray(out, coords=coords, dims=[aux1, SHindexBase.name])
+        daout = _unstack_aux(daout, aux1)
+        daout.name = name
+        daout.attrs.update(get_cfglobal())
+        daout.attrs["history"] = "Multiplication performed using b200 backend"
+        daout.attrs["comments"] = self._credits
+        return daout
+
+    # ---- shlib-only extras (xr_accessor.py:36-51,203-207 default to engine="shlib" for these) ----------------------------
+    def gaunt(self, *a, **k):
+        self._notImplemented("gaunt")
+
+    def gauntReal(self, *a, **k):
+        self._notImplemented("gauntReal")
+
+    def wigner3j(self, *a, **k):
+        self._notImplemented("wigner3j")
+
+    def p2s(self, *a, **k):
+        self._notImplemented("p2s")
+
+
+def _reject_unknown(kwargs, allowed):
+    bad = [k for k in kwargs if k not in allowed]
+    if bad:
+        raise TypeError(f"b200 backend: unknown keyword argument(s) {bad}; supported: {list(allowed)}")
 
 
 def register(name="b200", device=0):

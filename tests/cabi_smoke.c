@@ -29,11 +29,27 @@ int main(void) {
     if (rc != SHB200_OK) return 20;
     /* Y00 = 1 everywhere: coefficient vector (1,0,...,0) must synthesise to a grid of ones */
     double coef[9] = {1, 0, 0, 0, 0, 0, 0, 0, 0}, grid[32];
-    rc = shb200_synthesis_host(plan, 1, coef, 9, 1, grid, 32, 8, 1);
-    shb200_plan_destroy(plan);
-    if (rc != SHB200_OK) return 21;
+    rc = shb200_synthesis_host(plan, 1, coef, 9, 1, grid, 32, 8, 1, NULL);
+    if (rc != SHB200_OK) { shb200_plan_destroy(plan); return 21; }
     for (int i = 0; i < 32; ++i)
-        if (fabs(grid[i] - 1.0) > 1e-14) return 22;
+        if (fabs(grid[i] - 1.0) > 1e-14) { shb200_plan_destroy(plan); return 22; }
+    /* the same with a per-degree scale of 2 passed as a per-call option, into page-locked memory from the library's pool */
+    double scale[3] = {2.0, 2.0, 2.0};
+    shb200_call_opts o;
+    memset(&o, 0, sizeof o);
+    o.struct_size = (int32_t)sizeof o;
+    o.degree_scale = scale;
+    void* pin = NULL;
+    if (shb200_host_alloc((int64_t)sizeof grid, &pin) != SHB200_OK) { shb200_plan_destroy(plan); return 23; }
+    rc = shb200_synthesis_host(plan, 1, coef, 9, 1, (double*)pin, 32, 8, 1, &o);
+    char names[128];
+    shb200_plan_last_kernels(plan, names, (int32_t)sizeof names);
+    shb200_plan_destroy(plan);
+    if (rc != SHB200_OK) return 24;
+    for (int i = 0; i < 32; ++i)
+        if (fabs(((double*)pin)[i] - 2.0) > 1e-14) return 25;
+    if (shb200_host_free(pin) != SHB200_OK || shb200_host_trim() != SHB200_OK) return 26;
+    if (strstr(names, "k_pack") == NULL) return 27;
     printf("gpu: ok\n");
     return 0;
 }
