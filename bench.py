@@ -6,8 +6,9 @@ One step = one pass of the hot path over one batch: 64 random Stokes fields synt
 (SURVEY.md §8e.1): every rank owns its own 64 fields, no data-path collective, weak scaling.
 
   value    : device-resident round trips/s (inputs already in HBM), whole job, max-over-ranks time
-  e2e      : the same through the host-buffer C-ABI call the plugin makes (pinned host numpy in/out,
-             H2D + D2H inside the timed region)
+  e2e      : the same through the calls the plugin makes -- SHEngine.synthesis / .analysis with PLAIN (pageable) numpy
+             coefficients in, numpy out, H2D + D2H inside the timed region; beside it the all-pinned C-ABI variant, the
+             fused pipelined round trip (shb200_roundtrip_host) and the PCIe copy rates measured in the same run
   roofline : dominant kernel (Legendre stage, FP64 tensor pipe), algorithmic flops / CUDA-event time
   cpu_baseline : the shlib arithmetic (oracle/_ref, else the C port) on the host cores, bounded sample
 
@@ -84,8 +85,12 @@ class ClockSampler:
 def ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed ncu --set full capture."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["kernels"][kernel]
-        return d["dram_bytes_read"] + d["dram_bytes_write"]
+        for name in ("r02_traffic.json", "r01_traffic.json"):
+            path = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(path):
+                d = json.load(open(path))["kernels"][kernel]
+                return d["dram_bytes_read"] + d["dram_bytes_write"]
+        return None
     except Exception:
         return None
 
@@ -111,7 +116,7 @@ def cpu_sample(steps, warmup, per_step_scale=1.0):
         nthr = len(os.sched_getaffinity(0))      # torchrun exports OMP_NUM_THREADS=1: ask for every usable host thread explicitly
     except AttributeError:
         nthr = os.cpu_count() or 1
-    lon, lat, _ = S.gauss_grid(NLAT, NLON)
+    lon, lat, _ = S.gauss_grid(NLAT, NLON, nodes="numpy")     # the CPU arm never loads libshb200.so
     n, m = O.nm_index(NMAX)
     c = S.random_coefficients(NMAX, BATCH, kaula=True)
     rows = np.linspace(0, NLAT - 1, max(nthr, 2)).round().astype(int)       # >= 1 latitude row per thread (prange over rows)
@@ -239,6 +244,7 @@ def main():
         st = plan.stage_times()
         for k, v in st.items():
             acc[k] = acc.get(k, 0.0) + v / args.steps
+    kernels = plan.last_kernels()          # of the last device-resident analysis call
     L_rows = plan.info.nrows
     paired = L_rows < NLAT
     flops_leg = (1.0 if paired else 2.0) * nsh * NLAT * BATCH          # F_sym / F_alg Legendre term x batch
@@ -251,30 +257,118 @@ def main():
                 "symmetry": "mirror-latitude pairing used: F_sym = nsh*L per field" if paired else "no pairing: F_alg = 2*nsh*L per field",
                 "stages_ms": acc}
 
-    # ---- end to end through the host-buffer C-ABI calls (pinned numpy in / out) ------------------
-    grid_h = torch.empty((BATCH, NLAT, NLON), dtype=torch.float64).pin_memory()
-    out_h = torch.empty((BATCH, nsh), dtype=torch.float64).pin_memory()
-    cnp, gnp, onp = coef_h.numpy(), grid_h.numpy(), out_h.numpy()
+    # ---- FP64 peak re-measured on this box: cuBLAS DGEMM 8192^3 through torch (a library GEMM as yardstick only) --------
+    def dgemm_tflops():
+        n = 8192
+        a = torch.randn((n, n), dtype=torch.float64, device="cuda")
+        b = torch.randn((n, n), dtype=torch.float64, device="cuda")
+        torch.matmul(a, b)
+        t0_, t1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        t0_.record()
+        for _ in range(3):
+            torch.matmul(a, b)
+        t1_.record()
+        torch.cuda.synchronize()
+        return 3 * 2.0 * n ** 3 / (t0_.elapsed_time(t1_) * 1e-3) * 1e-12
 
-    def step_e2e():
-        plan.synthesis_host(BATCH, cnp.ctypes.data, nsh, 1, gnp.ctypes.data, NLAT * NLON, NLON, 1)
-        plan.analysis_host(BATCH, gnp.ctypes.data, NLAT * NLON, NLON, 1, onp.ctypes.data, nsh, 1)
+    dgemm = dgemm_tflops()
+    flops_step = 2.0 * flops_leg + 2.0 * 2.5 * NLAT * NLON * np.log2(NLON) * BATCH     # both directions: Legendre (F_sym) + FFT terms
+    roofline["fp64_peak_check"] = {"cublas_dgemm_8192_tflops": dgemm, "frac_vs_dgemm": achieved / dgemm,
+                                   "note": "cuBLAS DGEMM measured in this run; `peak` is the DMMA issue-rate microbenchmark (tools/fp64_peaks.cu)"}
+    roofline["whole_step"] = {"flops_per_step": flops_step, "achieved_tflops": flops_step / (ms_total / args.steps * 1e-3) * 1e-12,
+                              "frac": flops_step / (ms_total / args.steps * 1e-3) * 1e-12 / peak}
+    torch.cuda.empty_cache()
 
-    step_e2e()
-    ke = max(3, min(args.steps, 10))
-    barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(ke):
-        step_e2e()
-    torch.cuda.synchronize()
-    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e_val = world * BATCH * ke / float(dt.item())
+    # ---- PCIe copy rates of this box, measured in this run: pinned H2D, D2H and both at once (all ranks concurrently) ----
+    def pcie_rates():
+        nbytes = 512 << 20
+        hp = [torch.empty(nbytes // 8, dtype=torch.float64).pin_memory() for _ in range(2)]
+        dv = [torch.empty(nbytes // 8, dtype=torch.float64, device="cuda") for _ in range(2)]
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def run(h2d, d2h, reps=4):
+            barrier()
+            torch.cuda.synchronize()
+            t0_ = time.perf_counter()
+            for _ in range(reps):
+                if h2d:
+                    with torch.cuda.stream(s1):
+                        dv[0].copy_(hp[0], non_blocking=True)
+                if d2h:
+                    with torch.cuda.stream(s2):
+                        hp[1].copy_(dv[1], non_blocking=True)
+            torch.cuda.synchronize()
+            return reps * nbytes / (time.perf_counter() - t0_) * 1e-9
+
+        run(True, True, 1)
+        out = {"h2d_gbs": run(True, False), "d2h_gbs": run(False, True), "duplex_each_gbs": run(True, True)}
+        if world > 1:
+            for k in list(out):
+                v = torch.tensor([out[k]], dtype=torch.float64, device="cuda")
+                dist.all_reduce(v, op=dist.ReduceOp.SUM)
+                out[k + "_sum_all_ranks"] = float(v.item())
+        return out
+
+    pcie = pcie_rates()
+
+    # ---- end to end -------------------------------------------------------------------------------------------------
+    # (1) headline: the calls the plugin makes (xr_backend.py: SHEngine.synthesis / .analysis) with a plain pageable numpy
+    #     coefficient array in and numpy arrays out; the engine hands its results out of the library's page-locked pool.
+    # (2) all-pinned buffers straight through the C ABI (shb200_*_host), two calls.
+    # (3) the fused, pipelined round trip (shb200_roundtrip_host): same bytes over PCIe, both directions busy.
+    eng = sb.SHEngine(device=local)
+    c_page = S.random_coefficients(NMAX, BATCH, kaula=True, seed=S.SEED + rank)         # ordinary numpy memory
     nb_c, nb_g = BATCH * nsh * 8, BATCH * NLAT * NLON * 8
-    e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": nb_c + nb_g, "d2h_bytes_per_step": nb_c + nb_g, "steps": ke,
-           "roundtrip_max_rel_err": float((np.abs(onp - cnp).max(axis=1) / np.abs(cnp).max(axis=1)).max())}
+    ke = max(3, min(args.steps, 10))
+
+    def timed_e2e(fn):
+        fn()
+        barrier()
+        torch.cuda.synchronize()
+        t0_ = time.perf_counter()
+        for _ in range(ke):
+            res = fn()
+        torch.cuda.synchronize()
+        dt_ = torch.tensor([time.perf_counter() - t0_], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt_, op=dist.ReduceOp.MAX)
+        return world * BATCH * ke / float(dt_.item()), float(dt_.item()) / ke, res
+
+    def step_plugin():
+        g_ = eng.synthesis(c_page, lon=lon, lat=lat, nmax=NMAX)
+        return eng.analysis(g_, NMAX, lon, lat, quadrature="gauss")
+
+    v_plugin, t_plugin, a_plugin = timed_e2e(step_plugin)
+    e2e_err = float((np.abs(a_plugin - c_page).max(axis=1) / np.abs(c_page).max(axis=1)).max())
+    del a_plugin
+
+    grid_h = capi.pinned_empty((BATCH, NLAT, NLON))
+    out_h = capi.pinned_empty((BATCH, nsh))
+    c_pin = capi.pinned_empty((BATCH, nsh))
+    c_pin[...] = c_page
+
+    def step_pinned():
+        plan.synthesis_host(BATCH, c_pin.ctypes.data, nsh, 1, grid_h.ctypes.data, NLAT * NLON, NLON, 1)
+        plan.analysis_host(BATCH, grid_h.ctypes.data, NLAT * NLON, NLON, 1, out_h.ctypes.data, nsh, 1)
+
+    v_pinned, t_pinned, _ = timed_e2e(step_pinned)
+
+    def step_fused():
+        plan.roundtrip_host(BATCH, c_pin.ctypes.data, nsh, 1, grid_h.ctypes.data, NLAT * NLON, NLON, 1, out_h.ctypes.data, nsh, 1)
+
+    v_fused, t_fused, _ = timed_e2e(step_fused)
+    fused_err = float((np.abs(out_h - c_page).max(axis=1) / np.abs(c_page).max(axis=1)).max())
+    # floor of one step on this link: each direction carries coefficients + grid once; both directions can run at once
+    t_floor = (nb_c + nb_g) / (pcie["duplex_each_gbs"] * 1e9)
+    e2e = {"value": v_plugin, "unit": UNIT, "h2d_bytes_per_step": nb_c + nb_g, "d2h_bytes_per_step": nb_c + nb_g, "steps": ke,
+           "path": "SHEngine.synthesis + SHEngine.analysis, pageable numpy coefficients in, numpy out (page-locked pool)",
+           "ms_per_step": t_plugin * 1e3, "roundtrip_max_rel_err": e2e_err,
+           "pinned_c_abi": {"value": v_pinned, "ms_per_step": t_pinned * 1e3, "path": "shb200_synthesis_host + shb200_analysis_host, all buffers page-locked"},
+           "fused_roundtrip": {"value": v_fused, "ms_per_step": t_fused * 1e3, "path": "shb200_roundtrip_host (grid to the host and back, pipelined)", "roundtrip_max_rel_err": fused_err},
+           "pcie": pcie, "pcie_floor_ms_per_step": t_floor * 1e3,
+           "frac_of_pcie_floor": {"plugin": t_floor / t_plugin, "pinned_c_abi": t_floor / t_pinned, "fused_roundtrip": t_floor / t_fused}}
+    del grid_h, out_h, c_pin
 
     launches = args.steps * (plan.info.launches_synthesis + plan.info.launches_analysis)
     if rank == 0:
@@ -282,7 +376,7 @@ def main():
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": workload_config(world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                 "roofline": roofline, "roundtrip_max_rel_err": rt_err,
-                "dmma": bool(plan.info.dmma), "lon_fft": bool(plan.info.lon_fft)}
+                "dmma": bool(plan.info.dmma), "lon_fft": bool(plan.info.lon_fft), "kernels_last_call": kernels}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"], _ = cpu_sample(1, 0)
         print(json.dumps(line))

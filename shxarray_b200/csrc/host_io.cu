@@ -380,7 +380,8 @@ static int copy_out_bounced(HostIO& h, const ChunkView& v, OutRing& r) {
     return 0;
 }
 
-static int host_chunks(int batch) { return batch >= 32 ? 4 : (batch >= 16 ? 2 : 1); }
+// chunks of at least 16 fields: below 32 columns the Legendre stage leaves the tensor-core kernels
+static int host_chunks(int batch) { return std::max(1, std::min(4, batch / 16)); }
 
 // The pipeline.  which = 0: synthesis (in = coefficients, out = grid); 1: analysis (in = grid, out = coefficients);
 // 2: round trip (in = coefficients, mid = grid written to the host AND read back from it, out = coefficients).

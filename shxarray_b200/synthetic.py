@@ -28,10 +28,15 @@ def random_coefficients(nmax, batch, kaula=True, seed=SEED, nmin=0):
     return c
 
 
-def gauss_grid(nlat, nlon):
-    """Gauss-Legendre latitudes (degrees, ascending, exactly antisymmetric) and lon = arange(nlon)*360/nlon."""
-    from .capi import gauss_nodes
-    x, w = gauss_nodes(nlat)
+def gauss_grid(nlat, nlon, nodes="library"):
+    """Gauss-Legendre latitudes (degrees, ascending, exactly antisymmetric) and lon = arange(nlon)*360/nlon.
+    nodes="library": shb200_gauss_nodes (long double Newton); "numpy": numpy.polynomial.legendre.leggauss -- for processes
+    that must not load libshb200.so (the CPU reference arm of bench.py)."""
+    if nodes == "numpy":
+        x, w = np.polynomial.legendre.leggauss(nlat)
+    else:
+        from .capi import gauss_nodes
+        x, w = gauss_nodes(nlat)
     lat = np.rad2deg(np.arcsin(x))
     half = nlat // 2
     lat[nlat - half:] = -lat[:half][::-1]  # enforce bit-exact north/south symmetry
