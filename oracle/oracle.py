@@ -181,6 +181,15 @@ def analysis(grid, nmax, lon, lat, kind=None, nthreads=0, weight=None):
     return out
 
 
+def set_exact_trig(on):
+    """Diagnostic switch of the C port only (see shlib_port.c): trig arguments formed in long double instead of the
+    reference's doubly rounded k*lonr.  NOT reference behaviour; always switch it off again."""
+    lib, _ = _lib("port")
+    lib.port_set_exact_trig.argtypes = [C.c_int]
+    lib.port_set_exact_trig.restype = None
+    lib.port_set_exact_trig(1 if on else 0)
+
+
 def max_threads():
     if have_ref():
         lib, _ = _lib("ref")

@@ -90,6 +90,15 @@ static void ynm_init(port_ynm_t* y, int nsh, const int* n, const int* m) {
 }
 static void ynm_free(port_ynm_t* y) { free(y->wnn); free(y->wnm); free(y->pnm); free(y->cosm); free(y->sinm); }
 
+/* DIAGNOSTIC SWITCH, not reference behaviour.  The reference evaluates trig(k * lonr) with lonr = lon*pi/180 rounded to
+ * double and the product k*lonr rounded again (Ynm.hpp:114,127): at k ~ 2000 that argument is off by up to ~2e-12 rad,
+ * which is the largest systematic difference between shlib and any transform that uses exact DFT twiddles (SURVEY.md A.2:
+ * 2.3e-12 ... 3.8e-12 per basis function at nmax 2160).  With the switch on, the argument is formed in long double from
+ * the longitude in degrees, i.e. the basis functions shlib INTENDS; tests use it to show that the whole residual of the
+ * nmax-2160 white-noise analysis case is this argument rounding and nothing else. */
+static int g_exact_trig = 0;
+void port_set_exact_trig(int on) { g_exact_trig = on; }
+
 static void ynm_set(port_ynm_t* y, double lon, double lat, double* out) {
     if (lat != y->latprev) { /* Ynm.hpp:107-113 */
         double costheta = sin(lat * M_PI / 180.0);
@@ -97,6 +106,14 @@ static void ynm_set(port_ynm_t* y, double lon, double lat, double* out) {
         y->latprev = lat;
     }
     double lonr = lon * M_PI / 180.0; /* :114 */
+    if (g_exact_trig) {
+        const long double d2r = 3.141592653589793238462643383279503L / 180.0L;
+        for (int k = 0; k <= y->nmax; ++k) {
+            /* k*lon is exact in long double for the grids in use; reduce in degrees before converting */
+            long double a = fmodl((long double)k * (long double)lon, 360.0L) * d2r;
+            y->cosm[k] = (double)cosl(a); y->sinm[k] = (double)sinl(a);
+        }
+    } else
     for (int k = 0; k <= y->nmax; ++k) { y->cosm[k] = cos(k * lonr); y->sinm[k] = sin(k * lonr); } /* :127 */
     for (int i = 0; i < y->nsh; ++i) {
         int mm = y->m[i], am = mm < 0 ? -mm : mm;

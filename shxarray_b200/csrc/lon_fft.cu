@@ -627,7 +627,7 @@ static int launch_syn_fp(const Plan& p, const FP& fp, int NF, int nthreads, size
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fft::k_lon_syn_fft<FP>, nthreads, smem);
     static const int pf_env = getenv("SHB200_FFT_PREFETCH") ? atoi(getenv("SHB200_FFT_PREFETCH")) : 1;
     const int ahead = pf_env ? std::max(1, per_sm) * device_sm_count() : 0;
-    trace_kernel(p, FP::is_static ? (NF == 8 ? "k_lon_syn_fft<static,8>" : "k_lon_syn_fft<static>") : "k_lon_syn_fft<runtime>");
+    trace_kernel(p, FP::is_static ? (NF == 8 ? "k_lon_syn_fft<static/8>" : "k_lon_syn_fft<static>") : "k_lon_syn_fft<runtime>");
     fft::k_lon_syn_fft<FP><<<g, nthreads, smem, st>>>(p.t, fp, p.fft_perm, batch, p.G, grid, gs_b, gs_lat, gs_lon, ahead);
     return 0;
 }
@@ -643,7 +643,7 @@ static int launch_ana_fp(const Plan& p, const FP& fp, int NF, int nthreads, size
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fft::k_lon_ana_fft<FP>, nthreads, smem);
     static const int pf_env = getenv("SHB200_FFT_PREFETCH") ? atoi(getenv("SHB200_FFT_PREFETCH")) : 1;
     const int ahead = pf_env ? std::max(1, per_sm) * device_sm_count() : 0;
-    trace_kernel(p, FP::is_static ? (NF == 8 ? "k_lon_ana_fft<static,8>" : "k_lon_ana_fft<static>") : "k_lon_ana_fft<runtime>");
+    trace_kernel(p, FP::is_static ? (NF == 8 ? "k_lon_ana_fft<static/8>" : "k_lon_ana_fft<static>") : "k_lon_ana_fft<runtime>");
     fft::k_lon_ana_fft<FP><<<g, nthreads, smem, st>>>(p.t, fp, p.fft_perm, batch, grid, gs_b, gs_lat, gs_lon, p.G, ahead);
     return 0;
 }

@@ -607,8 +607,8 @@ def _r2_grid(tag, z):
     return g["lon"], g["lat"]
 
 
-R2_SYN = [("cfg3", "r2_syn_cfg3_b64.npz", ["k_pack_n", "k_leg_syn_tab<4>", "k_lon_syn_fft<static,8>"]),
-          ("cfg2", "r2_syn_cfg2_b240.npz", ["k_pack_n", "k_leg_syn_tab<4>", "k_lon_syn_fft<static,8>"]),
+R2_SYN = [("cfg3", "r2_syn_cfg3_b64.npz", ["k_pack_n", "k_leg_syn_tab<4>", "k_lon_syn_fft<static/8>"]),
+          ("cfg2", "r2_syn_cfg2_b240.npz", ["k_pack_n", "k_leg_syn_tab<4>", "k_lon_syn_fft<static/8>"]),
           ("n2160", "r2_syn_n2160_b16.npz", ["k_pack_n", "k_leg_syn_tab<1>", "k_lon_syn_fft<static>"])]
 
 
@@ -643,9 +643,9 @@ def test_r2_synthesis_headline_kernels_vs_oracle(tag, fname, kernels):
     plan.close()
 
 
-R2_ANA = [("cfg3", "r2_ana_cfg3_b64.npz", ["k_lon_ana_fft<static,8>", "k_leg_ana_tab<4>", "k_unpack_n"]),
-          ("cfg2", "r2_ana_cfg2_b240.npz", ["k_lon_ana_fft<static,8>", "k_leg_ana_tab<4>", "k_unpack_n"]),
-          ("n256", "r2_ana_n256_b4.npz", ["k_lon_ana_fft<static>", "k_leg_ana_small", "k_unpack_s"]),
+R2_ANA = [("cfg3", "r2_ana_cfg3_b64.npz", ["k_lon_ana_fft<static/8>", "k_leg_ana_tab<4>", "k_unpack_n"]),
+          ("cfg2", "r2_ana_cfg2_b240.npz", ["k_lon_ana_fft<static/8>", "k_leg_ana_tab<4>", "k_unpack_n"]),
+          ("n256", "r2_ana_n256_b4.npz", ["k_lon_ana_fft<runtime>", "k_leg_ana_small", "k_unpack_s"]),
           ("n2160", "r2_ana_n2160_b16.npz", ["k_lon_ana_fft<static>", "k_leg_ana_tab<1>", "k_unpack_n"])]
 
 
@@ -677,7 +677,33 @@ def test_r2_analysis_headline_kernels_vs_oracle(tag, fname, kernels):
         assert plan.info.dmma == 2
     got = out[:, torch.as_tensor(z["positions"], device="cuda")].cpu().numpy()
     err = np.abs(got - z["values"]).max(axis=1) / z["fieldmax"]
-    assert err.max() <= TOL, (tag, err.max(), int(err.argmax()))
+    if tag != "n2160":
+        assert err.max() <= TOL, (tag, err.max(), int(err.argmax()))
+    else:
+        # nmax 2160, WHITE data on a handful of points, 5' grid: the one case where shlib's own trig limits parity.  The
+        # reference evaluates cos/sin(fl(m * fl(lon*pi/180))) (Ynm.hpp:114,127): at m ~ 2000 the argument is off by up to
+        # ~2e-12 rad, and np.arange(0, 360, 1/12) longitudes are themselves off the equispaced values by up to 4e-14 deg
+        # (x m = 1.5e-12 rad).  SURVEY.md A.2 measured 2.3e-12 ... 3.8e-12 per basis function; white data on few points has
+        # no averaging, so that is what the coefficients show.  Tolerance here: 4e-12 (that bound).  The proof that nothing
+        # else contributes: the C port with its trig ARGUMENT formed in long double (diagnostic switch, everything else
+        # identical to the reference) is itself 1.1e-12 away from oracle/_ref on this case, and the GPU agrees with the
+        # port evaluated at the exactly equispaced longitudes to <= 1e-12.
+        assert err.max() <= 4e-12, (tag, err.max(), int(err.argmax()))
+        # columns j = 135 k: lon_j = 11.25 k degrees is exactly representable, so the port sees the true equispaced longitudes
+        cols2 = 135 * np.arange(0, 32, 2)
+        vals2 = np.random.default_rng(seed + 5).standard_normal((B, len(rows), len(cols2)))
+        grid.zero_()
+        grid[:, ri, torch.as_tensor(cols2, device="cuda")[None, :]] = torch.from_numpy(vals2).cuda()
+        plan.analysis_dev(B, grid.data_ptr(), grid.stride(0), grid.stride(1), 1, out.data_ptr(), nsh, 1, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert plan.last_kernels() == kernels
+        O.set_exact_trig(True)
+        try:
+            ex = O.analysis(vals2, nmax, lon[cols2], lat[rows], kind="port", weight=float(z["weight"]), nthreads=O.max_threads())
+        finally:
+            O.set_exact_trig(False)
+        ex_err = np.abs(out.cpu().numpy() - ex).max(axis=1) / np.abs(ex).max(axis=1)
+        assert ex_err.max() <= TOL, ("exact-argument port", ex_err)
     # normalisation sanity: the stored field maxima are those of the full GPU vectors
     gmax = out.abs().amax(dim=1).cpu().numpy()
     assert np.abs(gmax / z["fieldmax"] - 1).max() < 1e-9
