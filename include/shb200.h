@@ -136,7 +136,7 @@ int shb200_analysis(shb200_plan* plan, int32_t batch, const double* grid, int64_
  *     batch-fastest array) are gathered / scattered run by run, never copied as a flat span.
  *   - Page-locked buffers (cudaHostAlloc / cudaHostRegister / shb200_host_alloc) are DMA-ed directly; pageable memory
  *     goes through a ring of pinned bounce buffers filled / drained by a small team of host threads
- *     (SHB200_HOST_THREADS, default 4) so that host memcpy, H2D, kernels and D2H overlap.
+ *     (SHB200_HOST_THREADS, default min(8, cores); pieces of SHB200_BOUNCE_MIB = 8 MiB) so that host memcpy, H2D, kernels and D2H overlap.
  *   - When the batch axis is the slowest axis of both arrays, batches of >= 16 fields are cut into up to 4 chunks that
  *     flow through three streams (copy-in, kernels, copy-out): both PCIe directions run at once. */
 int shb200_synthesis_host(shb200_plan* plan, int32_t batch, const double* coef, int64_t cs_b, int64_t cs_nm,

@@ -91,7 +91,10 @@ class Team {
 static int host_threads() {
     static const int n = [] {
         const char* e = getenv("SHB200_HOST_THREADS");
-        int v = e ? atoi(e) : 4;
+        // measured on the B200 box (tools/e2e_sweep.py, profiles/r02_e2e_sweep.jsonl): 266 MB of pageable coefficients in,
+        // 570 MB out: 23 / 17 / 16.6 / 15.3 ms with 2 / 4 / 8 / 16 threads -- beyond 4 the PCIe link (both directions busy) is
+        // the limit; a pageable 570 MB grid in: 36 / 23 / 20 / 17 ms
+        int v = e ? atoi(e) : std::min(8, (int)std::max(1u, std::thread::hardware_concurrency()));
         return std::max(1, std::min(v, 64));
     }();
     return n;
@@ -223,7 +226,7 @@ struct HostIO {
 static size_t bounce_size() {
     static const size_t n = [] {
         const char* e = getenv("SHB200_BOUNCE_MIB");
-        const int v = e ? atoi(e) : 16;
+        const int v = e ? atoi(e) : 8;      // 4 MiB pieces: 14.2 ms, 16 MiB: 16.6 ms, 64 MiB: 16.1 ms for the call above (8 threads)
         return (size_t)std::max(1, std::min(v, 1024)) << 20;
     }();
     return n;
