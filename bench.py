@@ -158,6 +158,56 @@ def run_reference(args, rank):
 
 
 # --------------------------------------------------------------------------------------------------
+def cfg4_sharded(torch, dist, sb, S, rank, world, local, nmax=2160, reps=5):
+    """BASELINE config 4 on the N GPUs of the run: ONE nmax-2160 field on the 5' grid (2160 x 4320), synthesis sharded by
+    latitude rows, analysis sharded by orders m (distributed.ShardedSH: one ncclAllGather each), against the same
+    transform on one GPU.  Device time (CUDA events), max over ranks.  Extra keys of the N>1 bench line only."""
+    from shxarray_b200.distributed import ShardedSH
+    d = 180.0 / nmax
+    h = np.arange(d / 2, 90, d)
+    lat = np.concatenate([-h[::-1], h])
+    lon = np.arange(0, 360, d)
+    w = (d * np.pi / 180) ** 2 / (4 * np.pi)
+    lw = np.cos(lat * (np.pi / 180))
+    eng = sb.SHEngine(device=local)
+    sh = ShardedSH(eng)
+    c = torch.from_numpy(S.random_coefficients(nmax, 1, kaula=True)).cuda()
+
+    def timed(fn):
+        out = fn()
+        fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return out, float(t.item())
+
+    akw = dict(quadrature="weights", lat_weights=lw, weight=w)
+    f_sh, t_syn = timed(lambda: sh.synthesis_latsharded(c, lon, lat, nmax=nmax))
+    bytes_syn = sh.last_exchange_bytes
+    a_sh, t_ana = timed(lambda: sh.analysis_msharded(f_sh, nmax, lon, lat, **akw))
+    bytes_ana = sh.last_exchange_bytes
+    f_1, t_syn1 = timed(lambda: eng.synthesis(c, lon=lon, lat=lat, nmax=nmax))
+    a_1, t_ana1 = timed(lambda: eng.analysis(f_1, nmax, lon, lat, **akw))
+    a_on_sharded_grid = eng.analysis(f_sh, nmax, lon, lat, **akw)
+    ok = torch.tensor([float(torch.equal(a_sh, a_on_sharded_grid)), -float(((f_sh - f_1).abs().max() / f_1.abs().max()).item())],
+                      device="cuda", dtype=torch.float64)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    return {"workload": f"cfg4: ONE field nmax={nmax}, grid {len(lat)}x{len(lon)} (5'), sharded over {world} GPUs",
+            "synthesis_latsharded_ms": t_syn, "analysis_msharded_ms": t_ana, "synthesis_1gpu_ms": t_syn1, "analysis_1gpu_ms": t_ana1,
+            "speedup_synthesis": t_syn1 / t_syn, "speedup_analysis": t_ana1 / t_ana,
+            "allgather_bytes_synthesis": int(bytes_syn), "allgather_bytes_analysis": int(bytes_ana),
+            "analysis_bit_identical_to_1gpu": bool(ok[0].item() == 1.0), "synthesis_max_rel_diff_vs_1gpu": float(-ok[1].item()),
+            "collectives_per_transform": 1}
+
+
+# --------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -372,12 +422,21 @@ def main():
     del grid_h, out_h, c_pin
 
     launches = args.steps * (plan.info.launches_synthesis + plan.info.launches_analysis)
+    cfg4 = None
+    info_dmma, info_fft = bool(plan.info.dmma), bool(plan.info.lon_fft)
+    if world > 1:
+        plan.close()
+        del coef, gridbuf, coef_out, eng
+        torch.cuda.empty_cache()
+        cfg4 = cfg4_sharded(torch, dist, sb, S, rank, world, local)
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": workload_config(world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                 "roofline": roofline, "roundtrip_max_rel_err": rt_err,
-                "dmma": bool(plan.info.dmma), "lon_fft": bool(plan.info.lon_fft), "kernels_last_call": kernels}
+                "dmma": info_dmma, "lon_fft": info_fft, "kernels_last_call": kernels}
+        if cfg4 is not None:
+            line["cfg4_sharded"] = cfg4
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"], _ = cpu_sample(1, 0)
         print(json.dumps(line))

@@ -167,6 +167,23 @@ int shb200_multiply(shb200_plan* syn_a, shb200_plan* syn_b, shb200_plan* ana, in
                     const double* coef_a, int64_t as_b, int64_t as_nm, const double* coef_b, int64_t bs_b, int64_t bs_nm,
                     double* coef_out, int64_t os_b, int64_t os_nm, void* stream);
 
+/* ---- multi-GPU exchange formats (one process per GPU; the collective itself is the caller's: ncclAllGather) ----------
+ * m-order-sharded analysis (BASELINE config 4): rank r of W integrates the orders m = r, r+W, ... and
+ * emits only those, packed m-major:  packed[b*ps_b + off_j + 2(n - m_j) + cs],  m_j = r + jW,
+ * off_j = 2 [ j(nmax+1-r) - W j(j-1)/2 ],  cs = 0 cosine / 1 sine (the m = 0 sine entries are zeros).
+ * shb200_shard_size = elements per field of rank r's shard.  opts->shard_rank / shard_world select the shard
+ * (degree_scale is applied here).  After gathering the W shards (rank r's at packed_all + r*rank_stride),
+ * shb200_unpack_shards writes the nm vector of analysis.pyx:29 (position n^2+n+m) -- bit-identical to the unsharded call. */
+int64_t shb200_shard_size(int32_t nmax, int32_t rank, int32_t world);
+int shb200_analysis_packed(shb200_plan* plan, int32_t batch, const double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon,
+                           double* packed, int64_t ps_b, void* stream, const shb200_call_opts* opts);
+int shb200_unpack_shards(int32_t nmax, int32_t world, int32_t batch, const double* packed_all, int64_t rank_stride, int64_t ps_b,
+                         double* coef, int64_t cs_b, int64_t cs_nm, void* stream);
+/* Latitude-sharded synthesis: the gathered buffer src[r*rank_stride + b*src_b + i*nlon + j] holds row i
+ * of rank r; row_of_slot[r*rmax + i] (device, int32) is its latitude index in the full grid or -1 for padding. */
+int shb200_scatter_rows(int32_t batch, int32_t world, int32_t rmax, int32_t nlon, const double* src, int64_t rank_stride, int64_t src_b,
+                        const int32_t* row_of_slot, double* dst, int64_t dst_b, int64_t dst_lat, void* stream);
+
 /* Gauss-Legendre nodes x (ascending in latitude: x = sin(lat), south to north) and weights (sum = 2). */
 int shb200_gauss_nodes(int32_t n, double* x, double* w);
 

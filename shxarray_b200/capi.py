@@ -23,6 +23,7 @@ EXPORTS = [
     "shb200_synthesis", "shb200_analysis", "shb200_synthesis_host", "shb200_analysis_host", "shb200_multiply",
     "shb200_gauss_nodes", "shb200_debug_legendre", "shb200_plan_stage_times", "shb200_plan_last_kernels", "shb200_roundtrip_host",
     "shb200_host_alloc", "shb200_host_free", "shb200_host_trim", "shb200_debug_host_copy",
+    "shb200_shard_size", "shb200_analysis_packed", "shb200_unpack_shards", "shb200_scatter_rows",
 ]
 VERSION = 200
 
@@ -93,14 +94,19 @@ def lib():
     L.shb200_host_free.argtypes = [vp]
     L.shb200_host_trim.argtypes = []
     L.shb200_debug_host_copy.argtypes = [i32, vp, vp, vp, vp, i32, vp]
+    L.shb200_shard_size.argtypes = [i32, i32, i32]
+    L.shb200_analysis_packed.argtypes = [vp, i32, vp, i64, i64, i64, vp, i64, vp, po]
+    L.shb200_unpack_shards.argtypes = [i32, i32, i32, vp, i64, i64, vp, i64, i64, vp]
+    L.shb200_scatter_rows.argtypes = [i32, i32, i32, i32, vp, i64, i64, vp, vp, i64, i64, vp]
     L.shb200_multiply.argtypes = [vp, vp, vp, i32, vp, i64, i64, vp, i64, i64, vp, i64, i64, vp]
     L.shb200_plan_stage_times.argtypes = [vp, vp, i32]
     L.shb200_gauss_nodes.argtypes = [i32, vp, vp]
     L.shb200_debug_legendre.argtypes = [i32, i32, dbl, vp]
     for name in EXPORTS:
         f = getattr(L, name)
-        if name not in ("shb200_last_error", "shb200_plan_destroy"):
+        if name not in ("shb200_last_error", "shb200_plan_destroy", "shb200_shard_size"):
             f.restype = C.c_int
+    L.shb200_shard_size.restype = C.c_int64
     if L.shb200_version() != VERSION:
         raise SHB200Error(f"{LIB_PATH} is version {L.shb200_version()}, this binding needs {VERSION}: rebuild it (make -C shxarray_b200/csrc)")
     _lib = L
@@ -157,6 +163,22 @@ def pinned_empty(shape, dtype=np.float64):
     n = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
     blk = _PinnedBlock(max(n, 1))
     return np.asarray(blk)[:n].view(dtype).reshape(shape)
+
+
+def shard_size(nmax, rank, world):
+    """elements per field of rank's m-order shard (orders rank, rank+world, ...; cosine and sine interleaved)"""
+    n = int(lib().shb200_shard_size(int(nmax), int(rank), int(world)))
+    if n < 0:
+        raise ValueError("need nmax >= 0 and 0 <= rank < world")
+    return n
+
+
+def unpack_shards_dev(nmax, world, batch, all_ptr, rank_stride, ps_b, coef_ptr, cs_b, cs_nm, stream=0):
+    check(lib().shb200_unpack_shards(int(nmax), int(world), int(batch), all_ptr, rank_stride, ps_b, coef_ptr, cs_b, cs_nm, stream))
+
+
+def scatter_rows_dev(batch, world, rmax, nlon, src_ptr, rank_stride, src_b, row_of_slot_ptr, dst_ptr, dst_b, dst_lat, stream=0):
+    check(lib().shb200_scatter_rows(int(batch), int(world), int(rmax), int(nlon), src_ptr, rank_stride, src_b, row_of_slot_ptr, dst_ptr, dst_b, dst_lat, stream))
 
 
 def host_trim():
@@ -283,6 +305,11 @@ class Plan:
     def analysis_host(self, batch, grid_ptr, gs_b, gs_lat, gs_lon, coef_ptr, cs_b, cs_nm, degree_scale=None, order_shard=None):
         o, keep = _opts(degree_scale, order_shard, self.nmax)
         check(lib().shb200_analysis_host(self._h, batch, grid_ptr, gs_b, gs_lat, gs_lon, coef_ptr, cs_b, cs_nm, o))
+
+    def analysis_packed_dev(self, batch, grid_ptr, gs_b, gs_lat, gs_lon, packed_ptr, ps_b, order_shard, stream=0, degree_scale=None):
+        """analysis of this rank's orders only, output = the compact m-major shard (shb200_analysis_packed)"""
+        o, keep = _opts(degree_scale, order_shard, self.nmax)
+        check(lib().shb200_analysis_packed(self._h, batch, grid_ptr, gs_b, gs_lat, gs_lon, packed_ptr, ps_b, stream, o))
 
     def roundtrip_host(self, batch, coef_ptr, cs_b, cs_nm, grid_ptr, gs_b, gs_lat, gs_lon, out_ptr, os_b, os_nm,
                        syn_scale=None, ana_scale=None):

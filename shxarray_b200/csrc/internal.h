@@ -79,6 +79,7 @@ int device_sm_count();   // multiprocessors of the current device (cached per de
 
 void launch_pack(const Plan& p, int batch, const double* coef, int64_t cs_b, int64_t cs_nm, cudaStream_t st);
 void launch_unpack(const Plan& p, int batch, double* coef, int64_t cs_b, int64_t cs_nm, cudaStream_t st);
+void launch_pack_shard(const Plan& p, int batch, double* packed, int64_t ps_b, cudaStream_t st);   // shard.cu
 // Legendre stage
 void launch_legendre_syn(const Plan& p, cudaStream_t st);   // Cm -> G
 void launch_legendre_ana(const Plan& p, cudaStream_t st);   // G  -> Cm

@@ -418,6 +418,27 @@ int do_analysis(Plan& p, int batch, const double* grid, int64_t gs_b, int64_t gs
     return 0;
 }
 
+// analysis whose output is the rank's compact m-major shard (shard.cu) instead of the zero-padded nm vector
+int do_analysis_packed(Plan& p, int batch, const double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, double* packed, int64_t ps_b,
+                       cudaStream_t st, const CallOpts& o) {
+    if (p.quadrature == SHB200_QUAD_NONE) { set_error("analysis: plan was created without quadrature weights"); return SHB200_EINVAL; }
+    int rc = check_batch(p, batch);
+    if (rc) return rc;
+    SHB_CUDA(cudaSetDevice(p.device));
+    const bool tm = p.flags & SHB200_FLAG_TIMING;
+    CallScope scope(p, batch, st, o, 1);
+    if (tm) cudaEventRecord(p.ev[4], st);
+    rc = launch_lon_ana(p, batch, grid, gs_b, gs_lat, gs_lon, st);
+    if (rc) return rc;
+    if (tm) cudaEventRecord(p.ev[5], st);
+    launch_legendre_ana(p, st);
+    if (tm) cudaEventRecord(p.ev[6], st);
+    launch_pack_shard(p, batch, packed, ps_b, st);
+    if (tm) { cudaEventRecord(p.ev[7], st); p.timed_ana = true; }
+    SHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace shb
 
 using namespace shb;

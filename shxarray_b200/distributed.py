@@ -6,17 +6,19 @@ synthesis.pyx:179, analysis.pyx:128).  The path shards three ways (SURVEY.md §8
 * batch sharding  -- fields are independent (the dgemv/dger columns never mix: synthesis.pyx:183,
   analysis.pyx:136): every rank transforms its own contiguous slice of the batch, NO collective.
   This is what bench.py scales (weak scaling).
-* latitude sharding of a single (few-field) transform -- rows are independent in synthesis
-  (prange(nlat)); mirror latitude pairs stay on one rank so the E/O symmetry survives.  Synthesis needs no
-  reduction (optional all_gather of the grid rows); analysis produces per-rank partial quadrature sums that
-  one all_reduce(SUM) of the coefficient vector combines -- the only real exchange step of the path.
+* latitude sharding of a single (few-field) synthesis -- rows are independent (prange(nlat)); mirror latitude pairs stay
+  on one rank so the E/O symmetry survives.  Every rank synthesises its rows straight into its slot of a
+  [world, B, rmax, nlon] buffer; ONE all-gather (ncclAllGather, in place); one kernel (shb200_scatter_rows) puts the rows
+  where they belong in the [B, nlat, nlon] grid.  With ``gather=False`` the rows stay sharded and nothing is exchanged.
+* m-order sharding of a single analysis (BASELINE config 4, what north_star names) -- every rank holds the grid, runs the
+  cheap longitude stage for all rows and integrates only the orders m = rank (mod world) (interleaved because the work per
+  order is proportional to nmax-m+1).  It emits ONLY those orders, packed m-major (4.6 MB per rank at nmax 2160);
+  ONE all-gather of the shards (37 MB in total); one kernel (shb200_unpack_shards) writes the nm vector -- bit-identical to
+  the unsharded transform.  Latitude-sharded analysis (+ an all_reduce of partial sums) remains as the alternative for
+  grids that are already distributed by rows.
 
-* m-order sharding of a single analysis (what BASELINE's config 4 names) -- every rank holds the grid, runs the cheap
-  longitude stage for all rows and integrates only the orders m = rank (mod world) (interleaved because the work per
-  order is proportional to nmax-m+1); all other coefficients come out as exact zeros, so one all_reduce(SUM) -- a gather
-  in effect, 37 MB at nmax 2160 -- assembles the full vector bit-identically to the unsharded transform.
-
-The engine is injectable so the planner logic is testable on CPU (world_size 2, gloo) with the oracle.
+The engine is injectable so the planner logic is testable on CPU (world_size 2, gloo) with the oracle; the numpy
+functions below define the exchange formats (include/shb200.h) and serve those tests.
 """
 import numpy as np
 
@@ -69,6 +71,43 @@ def _lat_shard_indices(lat, world, rank):
     return np.asarray(idx, dtype=np.int64)
 
 
+# ---- exchange formats (numpy definitions; the CUDA kernels of csrc/shard.cu implement the same) -----------------------
+def shard_size(nmax, rank, world):
+    """elements per field of rank's m-order shard: orders rank, rank+world, ..., cosine and sine interleaved"""
+    return int(sum(2 * (nmax - m + 1) for m in range(rank, nmax + 1, world)))
+
+
+def pack_orders_np(coef, nmax, rank, world):
+    """[B, (nmax+1)^2] nm vector -> [B, shard_size] m-major shard of the orders m = rank (mod world):
+    element off_j + 2 (n - m_j) + cs  with  m_j = rank + j world  (include/shb200.h: shb200_analysis_packed)."""
+    coef = np.asarray(coef)
+    out = np.zeros((coef.shape[0], shard_size(nmax, rank, world)))
+    off = 0
+    for m in range(rank, nmax + 1, world):
+        n = np.arange(m, nmax + 1)
+        out[:, off:off + 2 * len(n):2] = coef[:, n * n + n + m]
+        if m > 0:
+            out[:, off + 1:off + 2 * len(n):2] = coef[:, n * n + n - m]
+        off += 2 * len(n)
+    return out
+
+
+def unpack_shards_np(gathered, nmax):
+    """[world, B, >= shard_size] gathered shards -> [B, (nmax+1)^2] in nm order (shb200_unpack_shards)."""
+    gathered = np.asarray(gathered)
+    W, B = gathered.shape[0], gathered.shape[1]
+    out = np.zeros((B, (nmax + 1) ** 2))
+    for r in range(W):
+        off = 0
+        for m in range(r, nmax + 1, W):
+            n = np.arange(m, nmax + 1)
+            out[:, n * n + n + m] = gathered[r, :, off:off + 2 * len(n):2]
+            if m > 0:
+                out[:, n * n + n - m] = gathered[r, :, off + 1:off + 2 * len(n):2]
+            off += 2 * len(n)
+    return out
+
+
 class _Dist:
     """Thin view of torch.distributed that degrades to a single rank when no process group exists."""
 
@@ -88,13 +127,30 @@ class _Dist:
     def rank(self):
         return self.dist.get_rank(self.group) if self.dist else 0
 
+    def all_gather_inplace(self, buf):
+        """buf [world, ...] with this rank's slot filled -> every slot filled.  ONE collective (ncclAllGather in place)."""
+        if self.world == 1:
+            return buf
+        mine = buf[self.rank]
+        try:
+            self.dist.all_gather_into_tensor(buf, mine, group=self.group)
+        except (RuntimeError, NotImplementedError):
+            # backends without the flat all-gather (older gloo): list form, then copy into place
+            parts = [buf[r].clone() for r in range(self.world)]
+            self.dist.all_gather(parts, mine.clone(), group=self.group)
+            for r in range(self.world):
+                buf[r].copy_(parts[r])
+        return buf
+
 
 class ShardedSH:
-    """Batch- and latitude-sharded transforms on top of an engine with the ``SHEngine`` array interface."""
+    """Batch-, latitude- and order-sharded transforms on top of an engine with the ``SHEngine`` array interface."""
 
     def __init__(self, engine, group=None):
         self.engine = engine
         self.d = _Dist(group)
+        self._slots = {}
+        self.last_exchange_bytes = 0      # bytes this rank contributed to + received from the last collective
 
     # ---- batch sharding: no collective -------------------------------------------------------------
     def local_batch(self, batch):
@@ -107,25 +163,54 @@ class ShardedSH:
     def analysis_batch(self, grid_local, nmax, lon, lat, **kw):
         return self.engine.analysis(grid_local, nmax, lon, lat, **kw)
 
-    # ---- latitude sharding of one transform ----------------------------------------------------------
+    # ---- latitude sharding of one synthesis ------------------------------------------------------------
+    def _row_slots(self, lat, device):
+        """(rows of every rank, rmax, row_of_slot int32 [world*rmax] on ``device`` or numpy)"""
+        W = self.d.world
+        key = (lat.tobytes(), W, str(device))
+        if key not in self._slots:
+            if len(self._slots) > 8:
+                self._slots.clear()
+            allrows = [lat_shard_indices(lat, W, r) for r in range(W)]
+            rmax = max(len(r) for r in allrows)
+            ros = np.full(W * rmax, -1, dtype=np.int32)
+            for r, rows in enumerate(allrows):
+                ros[r * rmax:r * rmax + len(rows)] = rows
+            if device is not None:
+                import torch
+                ros = torch.from_numpy(ros).to(device)
+            self._slots[key] = (allrows, rmax, ros)
+        return self._slots[key]
+
     def synthesis_latsharded(self, coef, lon, lat, gather=True, **kw):
         """coef replicated on every rank ([B, nsh]); each rank synthesises its latitude rows.  Returns the full grid
-        [B, nlat, nlon] on every rank when ``gather`` (one all_gather of row blocks), else (rows, local grid)."""
+        [B, nlat, nlon] on every rank when ``gather`` (one all-gather + one row scatter), else (rows, local grid)."""
         import torch
         lat = np.asarray(lat, dtype=np.float64)
-        rows = lat_shard_indices(lat, self.d.world, self.d.rank)
-        local = self.engine.synthesis(coef, lon=lon, lat=lat[rows], **kw)           # [B, nrows_local, nlon]
-        if not gather or self.d.world == 1:
-            return (rows, local) if not gather else _scatter_rows(local, [rows], len(lat))
-        is_t = hasattr(local, "is_cuda")
-        loc_t = local if is_t else torch.from_numpy(np.ascontiguousarray(local))
-        counts = [len(lat_shard_indices(lat, self.d.world, r)) for r in range(self.d.world)]
-        B, K = loc_t.shape[0], loc_t.shape[2]
-        bufs = [torch.empty((B, c, K), dtype=loc_t.dtype, device=loc_t.device) for c in counts]
-        self.d.dist.all_gather(bufs, loc_t.contiguous(), group=self.d.group)
-        allrows = [lat_shard_indices(lat, self.d.world, r) for r in range(self.d.world)]
-        full = _scatter_rows(bufs, allrows, len(lat))
-        return full if is_t else full.numpy()
+        W, rank = self.d.world, self.d.rank
+        is_t = hasattr(coef, "is_cuda")
+        allrows, rmax, ros = self._row_slots(lat, coef.device if is_t else None)
+        rows = allrows[rank]
+        if not gather:
+            return rows, self.engine.synthesis(coef, lon=lon, lat=lat[rows], **kw)
+        B = coef.shape[0] if coef.ndim == 2 else 1
+        K, L = len(lon), len(lat)
+        if is_t and hasattr(self.engine, "scatter_rows"):
+            buf = torch.empty((W, B, rmax, K), dtype=torch.float64, device=coef.device)
+            self.engine.synthesis(coef, lon=lon, lat=lat[rows], out=buf[rank][:, :len(rows), :], **kw)
+            self.d.all_gather_inplace(buf)
+            self.last_exchange_bytes = buf.numel() * 8
+            return self.engine.scatter_rows(buf, ros, L)
+        local = np.asarray(self.engine.synthesis(coef, lon=lon, lat=lat[rows], **kw))
+        buf = torch.zeros((W, B, rmax, K), dtype=torch.float64)
+        buf[rank][:, :len(rows), :] = torch.from_numpy(np.ascontiguousarray(local).reshape(B, len(rows), K))
+        self.d.all_gather_inplace(buf)
+        self.last_exchange_bytes = buf.numel() * 8
+        full = np.empty((B, L, K))
+        g = buf.numpy()
+        for r, rr in enumerate(allrows):
+            full[:, rr, :] = g[r][:, :len(rr), :]
+        return full
 
     def analysis_latsharded(self, grid, nmax, lon, lat, lat_weights, weight, **kw):
         """grid [B, nlat, nlon] replicated (or at least the rank's rows valid); every rank integrates its latitude rows
@@ -144,33 +229,30 @@ class ShardedSH:
         is_t = hasattr(part, "is_cuda")
         pt = part if is_t else torch.from_numpy(np.ascontiguousarray(part))
         self.d.dist.all_reduce(pt, op=self.d.dist.ReduceOp.SUM, group=self.d.group)
+        self.last_exchange_bytes = pt.numel() * 8
         return pt if is_t else pt.numpy()
 
-
+    # ---- m-order sharding of one analysis ----------------------------------------------------------------
     def analysis_msharded(self, grid, nmax, lon, lat, **kw):
-        """grid [B, nlat, nlon] replicated on every rank; rank r integrates the orders m = r (mod world)
-        (shb200_plan_set_order_shard) and one all_reduce(SUM) over NVLink gathers the disjoint shards."""
+        """grid [B, nlat, nlon] replicated on every rank; rank r integrates the orders m = r (mod world) and emits only
+        those (compact m-major shard); ONE all-gather over NVLink; one unpack kernel writes the nm vector.  Bit-identical
+        to the unsharded analysis."""
         import torch
-        part = self.engine.analysis(grid, nmax, lon, lat, order_shard=(self.d.rank, self.d.world), **kw)
-        if self.d.world == 1:
-            return part
-        is_t = hasattr(part, "is_cuda")
-        pt = part if is_t else torch.from_numpy(np.ascontiguousarray(part))
-        self.d.dist.all_reduce(pt, op=self.d.dist.ReduceOp.SUM, group=self.d.group)
-        return pt if is_t else pt.numpy()
-
-
-def _scatter_rows(blocks, rows_per_rank, nlat):
-    import torch
-    if not isinstance(blocks, (list, tuple)):
-        blocks = [blocks]
-    b0 = blocks[0]
-    if hasattr(b0, "is_cuda"):
-        full = torch.empty((b0.shape[0], nlat, b0.shape[2]), dtype=b0.dtype, device=b0.device)
-        for blk, rows in zip(blocks, rows_per_rank):
-            full[:, torch.as_tensor(rows, device=b0.device), :] = blk
-        return full
-    full = np.empty((b0.shape[0], nlat, b0.shape[2]), dtype=b0.dtype)
-    for blk, rows in zip(blocks, rows_per_rank):
-        full[:, rows, :] = blk
-    return full
+        W, rank = self.d.world, self.d.rank
+        smax = shard_size(nmax, 0, W)                 # rank 0 owns m = 0: the largest shard
+        is_t = hasattr(grid, "is_cuda")
+        B = grid.shape[0]
+        if is_t and hasattr(self.engine, "unpack_shards"):
+            buf = torch.empty((W, B, smax), dtype=torch.float64, device=grid.device)
+            self.engine.analysis_packed(grid, nmax, lon, lat, (rank, W), buf[rank], **kw)
+            self.d.all_gather_inplace(buf)
+            self.last_exchange_bytes = buf.numel() * 8
+            return self.engine.unpack_shards(buf, nmax)
+        # numpy engines (CPU tests with the oracle): same exchange format through the numpy definitions above
+        part = np.asarray(self.engine.analysis(grid, nmax, lon, lat, order_shard=(rank, W), **kw))
+        buf = torch.zeros((W, B, smax), dtype=torch.float64)
+        mine = pack_orders_np(part, nmax, rank, W)
+        buf[rank][:, :mine.shape[1]] = torch.from_numpy(mine)
+        self.d.all_gather_inplace(buf)
+        self.last_exchange_bytes = buf.numel() * 8
+        return unpack_shards_np(buf.numpy(), nmax)

@@ -371,6 +371,17 @@ class SHEngine:
         return out
 
     # ------------------------------------------------------------------------------------------
+    def _analysis_plan(self, nmax, lon, lat, B, quadrature, lat_weights, weight, flags):
+        if quadrature == "shlib":
+            q, wgt, lw = capi.QUAD_SHLIB, analysis_weight_shlib(lon, lat), None
+        elif quadrature == "gauss":
+            q, wgt, lw = capi.QUAD_LATWEIGHTS, 1.0 / (2.0 * len(lon)), gauss_lat_weights(lat)
+        elif quadrature == "weights":
+            q, wgt, lw = capi.QUAD_LATWEIGHTS, (1.0 if weight is None else float(weight)), np.asarray(lat_weights, dtype=np.float64)
+        else:
+            raise ValueError("quadrature must be 'shlib', 'gauss' or 'weights'")
+        return self.get_plan(nmax, lat, lon, B, quadrature=q, weight=wgt, lat_weights=lw, flags=flags)
+
     def analysis(self, grid, nmax, lon, lat, quadrature="shlib", lat_weights=None, weight=None, layout="batch_first",
                  out=None, flags=None, degree_scale=None, order_shard=None):
         """Spherical-harmonic analysis of a batch of lon/lat grids (analysis.pyx:31-139).
@@ -404,15 +415,7 @@ class SHEngine:
             ok = grid.shape[0] == L and grid.shape[1] == K
         if not ok:
             raise ValueError("grid shape does not match lon/lat")
-        if quadrature == "shlib":
-            q, wgt, lw = capi.QUAD_SHLIB, analysis_weight_shlib(lon, lat), None
-        elif quadrature == "gauss":
-            q, wgt, lw = capi.QUAD_LATWEIGHTS, 1.0 / (2.0 * K), gauss_lat_weights(lat)
-        elif quadrature == "weights":
-            q, wgt, lw = capi.QUAD_LATWEIGHTS, (1.0 if weight is None else float(weight)), np.asarray(lat_weights, dtype=np.float64)
-        else:
-            raise ValueError("quadrature must be 'shlib', 'gauss' or 'weights'")
-        plan = self.get_plan(nmax, lat, lon, B, quadrature=q, weight=wgt, lat_weights=lw, flags=flags)
+        plan = self._analysis_plan(nmax, lon, lat, B, quadrature, lat_weights, weight, flags)
         nsh = (nmax + 1) ** 2
         if tor:
             import torch
@@ -451,6 +454,50 @@ class SHEngine:
         return out
 
 
+    # ---- multi-GPU exchange helpers (device tensors; distributed.ShardedSH drives them) --------------------------------
+    def analysis_packed(self, grid, nmax, lon, lat, order_shard, out, quadrature="shlib", lat_weights=None, weight=None,
+                        flags=None, degree_scale=None):
+        """Analysis of the orders m = rank (mod world) only; ``out`` [B, >= shard_size] (torch CUDA, last axis contiguous)
+        receives this rank's compact m-major shard (shb200_analysis_packed).  grid: torch CUDA [B, nlat, nlon]."""
+        import torch
+        lon = np.ascontiguousarray(lon, dtype=np.float64)
+        lat = np.ascontiguousarray(lat, dtype=np.float64)
+        B = grid.shape[0]
+        if tuple(grid.shape[1:]) != (len(lat), len(lon)) or out.shape[0] != B or out.stride(1) != 1:
+            raise ValueError("analysis_packed: grid must be [B, nlat, nlon] and out [B, S] with a contiguous last axis")
+        plan = self._analysis_plan(nmax, lon, lat, B, quadrature, lat_weights, weight, flags)
+        if B > plan.max_batch:
+            raise ValueError("analysis_packed: batch exceeds one plan call")
+        stream = torch.cuda.current_stream(grid.device).cuda_stream
+        plan.analysis_packed_dev(B, grid.data_ptr(), grid.stride(0), grid.stride(1), grid.stride(2), out.data_ptr(), out.stride(0),
+                                 order_shard, stream, degree_scale=degree_scale)
+        self.launches += plan.info.launches_analysis
+        return out
+
+    def unpack_shards(self, gathered, nmax, out=None):
+        """gathered: torch CUDA [world, B, S] of m-major shards (all ranks) -> [B, (nmax+1)^2] in nm order."""
+        import torch
+        W, B, _ = gathered.shape
+        if out is None:
+            out = torch.empty((B, (nmax + 1) ** 2), dtype=torch.float64, device=gathered.device)
+        stream = torch.cuda.current_stream(gathered.device).cuda_stream
+        capi.unpack_shards_dev(nmax, W, B, gathered.data_ptr(), gathered.stride(0), gathered.stride(1), out.data_ptr(), out.stride(0), out.stride(1), stream)
+        self.launches += 1
+        return out
+
+    def scatter_rows(self, gathered, row_of_slot, nlat, out=None):
+        """gathered: torch CUDA [world, B, rmax, nlon] row blocks of all ranks; row_of_slot: int32 CUDA [world*rmax]
+        (latitude index or -1) -> [B, nlat, nlon]."""
+        import torch
+        W, B, rmax, K = gathered.shape
+        if out is None:
+            out = torch.empty((B, nlat, K), dtype=torch.float64, device=gathered.device)
+        stream = torch.cuda.current_stream(gathered.device).cuda_stream
+        capi.scatter_rows_dev(B, W, rmax, K, gathered.data_ptr(), gathered.stride(0), gathered.stride(1), row_of_slot.data_ptr(),
+                              out.data_ptr(), out.stride(0), out.stride(1), stream)
+        self.launches += 1
+        return out
+
     # ------------------------------------------------------------------------------------------
     def roundtrip(self, coef, nmax, lon, lat, quadrature="gauss", lat_weights=None, weight=None, grid_out=None, out=None):
         """Synthesis to the grid AND analysis of that grid in one pipelined call on host arrays (shb200_roundtrip_host):
@@ -465,15 +512,7 @@ class SHEngine:
         if min(coef.strides) < 0:
             coef = np.ascontiguousarray(coef)
         B, L, K = coef.shape[0], len(lat), len(lon)
-        if quadrature == "shlib":
-            q, wgt, lw = capi.QUAD_SHLIB, analysis_weight_shlib(lon, lat), None
-        elif quadrature == "gauss":
-            q, wgt, lw = capi.QUAD_LATWEIGHTS, 1.0 / (2.0 * K), gauss_lat_weights(lat)
-        elif quadrature == "weights":
-            q, wgt, lw = capi.QUAD_LATWEIGHTS, (1.0 if weight is None else float(weight)), np.asarray(lat_weights, dtype=np.float64)
-        else:
-            raise ValueError("quadrature must be 'shlib', 'gauss' or 'weights'")
-        plan = self.get_plan(nmax, lat, lon, B, quadrature=q, weight=wgt, lat_weights=lw)
+        plan = self._analysis_plan(nmax, lon, lat, B, quadrature, lat_weights, weight, None)
         if grid_out is None:
             grid_out = capi.pinned_empty((B, L, K))
         if out is None:

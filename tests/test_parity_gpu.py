@@ -821,3 +821,69 @@ def test_plans_are_shared_safely_by_threads(engine):
     one = np.full((2, 1), 2.0)
     p1 = engine.multiply(a, 32, one, 0)
     assert np.abs(p1 - 2.0 * a).max() < 1e-12
+
+
+# ---- multi-GPU exchange formats (csrc/shard.cu), all ranks emulated on one device ------------------------------------------
+@pytest.mark.parametrize("nmax,B,flags", [(64, 3, 0), (200, 40, 0), (200, 40, capi.FLAG_NO_PTABLE), (95, 1, 0)])
+def test_packed_order_shards_gather_to_the_unsharded_analysis(engine, nmax, B, flags):
+    """shb200_analysis_packed + shb200_unpack_shards: the W compact m-major shards, gathered, are bit-identical to the
+    unsharded analysis (analysis.pyx:29 positions); the shard layout is the numpy definition of distributed.py."""
+    import torch
+    from shxarray_b200 import distributed as D
+    g = sb.lonlat_grid(nmax, gtype="regular_lon0")
+    f = torch.from_numpy(np.random.default_rng(18).standard_normal((B, len(g["lat"]), len(g["lon"])))).cuda()
+    full = engine.analysis(f, nmax, g["lon"], g["lat"], flags=flags)
+    scale = np.linspace(0.5, 1.5, nmax + 1)
+    full_scaled = engine.analysis(f, nmax, g["lon"], g["lat"], flags=flags, degree_scale=scale)
+    for world in (1, 2, 3, 8):
+        smax = D.shard_size(nmax, 0, world)
+        for r in range(world):
+            assert capi.shard_size(nmax, r, world) == D.shard_size(nmax, r, world) <= smax
+        buf = torch.full((world, B, smax + 3), float("nan"), dtype=torch.float64, device="cuda")     # padded stride on purpose
+        for r in range(world):
+            engine.analysis_packed(f, nmax, g["lon"], g["lat"], (r, world), buf[r], flags=flags)
+        torch.cuda.synchronize()
+        for r in range(world):
+            ref_shard = D.pack_orders_np(full.cpu().numpy(), nmax, r, world)
+            assert np.array_equal(buf[r, :, :ref_shard.shape[1]].cpu().numpy(), ref_shard)
+        got = engine.unpack_shards(buf, nmax)
+        assert torch.equal(got, full)
+        assert np.array_equal(D.unpack_shards_np(buf.cpu().numpy(), nmax), full.cpu().numpy())
+        # fused per-degree scale travels with the shard
+        for r in range(world):
+            engine.analysis_packed(f, nmax, g["lon"], g["lat"], (r, world), buf[r], flags=flags, degree_scale=scale)
+        assert torch.equal(engine.unpack_shards(buf, nmax), full_scaled)
+        # strided destination (nm-first array)
+        outT = torch.empty(((nmax + 1) ** 2, B), dtype=torch.float64, device="cuda")
+        engine.unpack_shards(buf, nmax, out=outT.T)
+        assert torch.equal(outT.T, full_scaled)
+
+
+@pytest.mark.parametrize("nmax,B,gtype", [(64, 3, "regular"), (200, 20, "gauss"), (95, 1, "regular_lon0")])
+def test_latitude_shards_scatter_to_the_full_grid(engine, nmax, B, gtype):
+    """shb200_scatter_rows after the all-gather of row blocks: every rank's rows land at their latitude index; the
+    sharded synthesis equals the one-GPU synthesis (rows are independent: synthesis.pyx:179)."""
+    import torch
+    from shxarray_b200 import distributed as D
+    g = sb.lonlat_grid(nmax, gtype=gtype)
+    lon, lat = g["lon"], g["lat"]
+    c = torch.from_numpy(S.random_coefficients(nmax, B, kaula=False, seed=77)).cuda()
+    full = engine.synthesis(c, lon=lon, lat=lat, nmax=nmax)
+    for world in (1, 2, 5, 8):
+        allrows = [D.lat_shard_indices(lat, world, r) for r in range(world)]
+        rmax = max(len(r) for r in allrows)
+        ros = np.full(world * rmax, -1, dtype=np.int32)
+        buf = torch.full((world, B, rmax, len(lon)), float("nan"), dtype=torch.float64, device="cuda")
+        for r, rows in enumerate(allrows):
+            ros[r * rmax:r * rmax + len(rows)] = rows
+            if len(rows):
+                engine.synthesis(c, lon=lon, lat=lat[rows], nmax=nmax, out=buf[r][:, :len(rows), :])
+        got = engine.scatter_rows(buf, torch.from_numpy(ros).cuda(), len(lat))
+        assert not torch.isnan(got).any()
+        assert per_field_err(got.cpu().numpy(), full.cpu().numpy()) <= 1e-13
+    # world 1 through the planner object itself (no process group): device path end to end
+    sh = D.ShardedSH(engine)
+    assert torch.equal(sh.synthesis_latsharded(c, lon, lat, nmax=nmax), full)
+    q = "gauss" if gtype == "gauss" else "shlib"
+    a1 = engine.analysis(full, nmax, lon, lat, quadrature=q)
+    assert torch.equal(sh.analysis_msharded(full, nmax, lon, lat, quadrature=q), a1)
