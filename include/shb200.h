@@ -167,6 +167,39 @@ int shb200_multiply(shb200_plan* syn_a, shb200_plan* syn_b, shb200_plan* ana, in
                     const double* coef_a, int64_t as_b, int64_t as_nm, const double* coef_b, int64_t bs_b, int64_t bs_nm,
                     double* coef_out, int64_t os_b, int64_t os_nm, void* stream);
 
+/* Grid-space operator  out = analysis_planA( mask x synthesis_planS(coef) ), the grid kept on the device:  the ocean
+ * function of the sea-level equation applied to a load (replaces SpectralSeaLevelSolver.oceanf, spectralsealevel.py:97-104,
+ * an O(nsh^2) product-to-sum matrix limited to nmax <= 150), basin masks (geom/polygons.py), any pointwise weight.
+ * mask: ONE device-resident [nlat, nlon] field, element (i,j) at mask[i*ms_lat + j*ms_lon], shared by the batch.
+ * syn_opts / ana_opts: per-degree scales fused into either transform (Love-number kernels: geoid, uplift). */
+int shb200_apply_mask(shb200_plan* syn, shb200_plan* ana, int32_t batch, const double* coef, int64_t cs_b, int64_t cs_nm,
+                      const double* mask, int64_t ms_lat, int64_t ms_lon, double* coef_out, int64_t os_b, int64_t os_nm,
+                      void* stream, const shb200_call_opts* syn_opts, const shb200_call_opts* ana_opts);
+
+/* ---- data formats either side of the transform, on the device --------------------------------------
+ * shb200_gfc_parse: the record block of an ICGEM ("gfc", D exponents allowed: io/icgem.py:94-128) or GRACE GSM ("GRCOF2",
+ * io/gsmv6.py:66-90) coefficient file -> dense nm vector cnm[(nmax+1)^2] (position n^2+n+m; sine terms at -m), optional
+ * sigcnm (with_sigma: columns 6/7) and `present` counts per position (a count > 1 is a duplicated record).  text: the file's
+ * bytes on the device.  Records with n > nmax are skipped.  Decimal conversion is correctly rounded (identical to strtod /
+ * Python float()); lines this kernel cannot decide are NOT stored: their byte offsets go to fallback_offsets (first
+ * fallback_capacity of them) for the host to convert.  stats (device, uint64[4]) = records stored, records skipped (n > nmax),
+ * lines handed back, reserved.  Outputs are zeroed by the call. */
+int shb200_gfc_parse(const char* text, int64_t nbytes, const char* record_key, int32_t d_exponent, int32_t nmax, int32_t with_sigma,
+                     double* cnm, double* sigcnm, int32_t* present, uint64_t* stats, int64_t* fallback_offsets, int32_t fallback_capacity,
+                     void* stream);
+/* tokens text[start[i] .. stop[i]) -> doubles (ok[i] = 0: not decided here); the converter of shb200_gfc_parse on its own */
+int shb200_parse_floats(const char* text, const int64_t* start, const int64_t* stop, int64_t ntokens, double* out, uint8_t* ok, void* stream);
+/* (n, m, value) records in any order -> dense nm vectors: coef[b*cs_b + (n^2+n+m)*cs_nm] = values[b*vs_b + k*vs_k] */
+int shb200_scatter_nm(const int32_t* n, const int32_t* m, const double* values, int64_t vs_b, int64_t vs_k, int64_t nrecords, int32_t batch,
+                      int32_t nmax, double* coef, int64_t cs_b, int64_t cs_nm, void* stream);
+/* Polygons -> 0/1 grid masks (geom/polygons.py:47-93: grid points contained in each polygon, planar lon/lat), ready for
+ * shb200_analysis.  All rings of all polygons in vx/vy (device); ring r = vertices ring_start[r] .. ring_start[r+1]-1 (closed
+ * implicitly); polygon p = rings poly_ring[p] .. poly_ring[p+1]-1, even-odd rule (holes, multi-part).  wrap_lon: grid longitudes
+ * are mapped to [-180, 180) first (:76-81).  mask element (p,i,j) at mask[p*ms_p + i*ms_lat + j*ms_lon]. */
+int shb200_polygon_mask(const double* vx, const double* vy, const int32_t* ring_start, const int32_t* poly_ring, int32_t npoly,
+                        const double* lon, const double* lat, int32_t nlat, int32_t nlon, int32_t wrap_lon,
+                        double* mask, int64_t ms_p, int64_t ms_lat, int64_t ms_lon, void* stream);
+
 /* ---- multi-GPU exchange formats (one process per GPU; the collective itself is the caller's: ncclAllGather) ----------
  * m-order-sharded analysis (BASELINE config 4): rank r of W integrates the orders m = r, r+W, ... and
  * emits only those, packed m-major:  packed[b*ps_b + off_j + 2(n - m_j) + cs],  m_j = r + jW,

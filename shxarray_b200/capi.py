@@ -23,7 +23,8 @@ EXPORTS = [
     "shb200_synthesis", "shb200_analysis", "shb200_synthesis_host", "shb200_analysis_host", "shb200_multiply",
     "shb200_gauss_nodes", "shb200_debug_legendre", "shb200_plan_stage_times", "shb200_plan_last_kernels", "shb200_roundtrip_host",
     "shb200_host_alloc", "shb200_host_free", "shb200_host_trim", "shb200_debug_host_copy",
-    "shb200_shard_size", "shb200_analysis_packed", "shb200_unpack_shards", "shb200_scatter_rows",
+    "shb200_shard_size", "shb200_analysis_packed", "shb200_unpack_shards", "shb200_scatter_rows", "shb200_apply_mask",
+    "shb200_gfc_parse", "shb200_parse_floats", "shb200_scatter_nm", "shb200_polygon_mask",
 ]
 VERSION = 200
 
@@ -98,6 +99,11 @@ def lib():
     L.shb200_analysis_packed.argtypes = [vp, i32, vp, i64, i64, i64, vp, i64, vp, po]
     L.shb200_unpack_shards.argtypes = [i32, i32, i32, vp, i64, i64, vp, i64, i64, vp]
     L.shb200_scatter_rows.argtypes = [i32, i32, i32, i32, vp, i64, i64, vp, vp, i64, i64, vp]
+    L.shb200_gfc_parse.argtypes = [vp, i64, C.c_char_p, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp]
+    L.shb200_parse_floats.argtypes = [vp, vp, vp, i64, vp, vp, vp]
+    L.shb200_scatter_nm.argtypes = [vp, vp, vp, i64, i64, i64, i32, i32, vp, i64, i64, vp]
+    L.shb200_polygon_mask.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, i32, i32, vp, i64, i64, i64, vp]
+    L.shb200_apply_mask.argtypes = [vp, vp, i32, vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, po, po]
     L.shb200_multiply.argtypes = [vp, vp, vp, i32, vp, i64, i64, vp, i64, i64, vp, i64, i64, vp]
     L.shb200_plan_stage_times.argtypes = [vp, vp, i32]
     L.shb200_gauss_nodes.argtypes = [i32, vp, vp]
@@ -310,6 +316,13 @@ class Plan:
         """analysis of this rank's orders only, output = the compact m-major shard (shb200_analysis_packed)"""
         o, keep = _opts(degree_scale, order_shard, self.nmax)
         check(lib().shb200_analysis_packed(self._h, batch, grid_ptr, gs_b, gs_lat, gs_lon, packed_ptr, ps_b, stream, o))
+
+    def apply_mask_dev(self, ana, batch, coef_ptr, cs_b, cs_nm, mask_ptr, ms_lat, ms_lon, out_ptr, os_b, os_nm, stream=0,
+                       syn_scale=None, ana_scale=None):
+        """out = ana.analysis(mask x self.synthesis(coef)) with the grid kept on the device (shb200_apply_mask)"""
+        o1, k1 = _opts(syn_scale, None, self.nmax)
+        o2, k2 = _opts(ana_scale, None, ana.nmax)
+        check(lib().shb200_apply_mask(self._h, ana._h, batch, coef_ptr, cs_b, cs_nm, mask_ptr, ms_lat, ms_lon, out_ptr, os_b, os_nm, stream, o1, o2))
 
     def roundtrip_host(self, batch, coef_ptr, cs_b, cs_nm, grid_ptr, gs_b, gs_lat, gs_lon, out_ptr, os_b, os_nm,
                        syn_scale=None, ana_scale=None):

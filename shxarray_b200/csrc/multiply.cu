@@ -12,9 +12,60 @@ __global__ void k_pointwise_mul(double* __restrict__ a, const double* __restrict
     for (; i < n; i += stride) a[i] *= b[i];
 }
 
+// grid[b][i] *= mask[i]  (mask: one [nlat, nlon] field with its own strides, shared by the batch)
+__global__ void __launch_bounds__(256) k_mask_mul(double* __restrict__ g, const double* __restrict__ mask, int nlat, int nlon, int64_t ms_lat, int64_t ms_lon,
+                                                  int64_t per, int batch) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= per) return;
+    const int il = (int)(i / nlon), ik = (int)(i - (int64_t)il * nlon);
+    const double w = mask[il * ms_lat + ik * ms_lon];
+    for (int b = 0; b < batch; ++b) g[(int64_t)b * per + i] *= w;
+}
+
+static int grow_mul_grid(Plan& pc, int64_t need) {
+    if (pc.mul_grid_elems < need) {
+        if (pc.mul_grid) { SHB_CUDA(cudaDeviceSynchronize()); cudaFree(pc.mul_grid); }
+        pc.mul_grid = nullptr; pc.mul_grid_elems = 0;
+        SHB_CUDA(cudaMalloc((void**)&pc.mul_grid, sizeof(double) * need));
+        pc.mul_grid_elems = need;
+    }
+    return 0;
+}
+
 }  // namespace shb
 
 using namespace shb;
+
+// Grid-space operator  out = analysis( mask x synthesis(coef) ):  the ocean function of the sea-level equation applied to a
+// load (spectralsealevel.py:97-104 does it with an O(nsh^2) product-to-sum matrix limited to nmax <= 150), basin masks, any
+// pointwise weight.  The grid never leaves HBM; per-degree scales (Love-number kernels) ride on either transform.
+extern "C" int shb200_apply_mask(shb200_plan* syn, shb200_plan* ana, int32_t batch, const double* coef, int64_t cs_b, int64_t cs_nm,
+                                 const double* mask, int64_t ms_lat, int64_t ms_lon, double* coef_out, int64_t os_b, int64_t os_nm,
+                                 void* stream, const shb200_call_opts* syn_opts, const shb200_call_opts* ana_opts) {
+    if (!syn || !ana || !coef || !mask || !coef_out) { set_error("apply_mask: null argument"); return SHB200_EINVAL; }
+    Plan& pa = syn->p; Plan& pc = ana->p;
+    if (pa.mode != SHB200_MODE_GRID || pa.nlat != pc.nlat || pa.nlon != pc.nlon || pa.device != pc.device) {
+        set_error("apply_mask: the two plans must share one lon/lat grid and device");
+        return SHB200_EINVAL;
+    }
+    if (batch < 1 || batch > pa.maxB || batch > pc.maxB) { set_error("apply_mask: batch exceeds a plan's max_batch"); return SHB200_EINVAL; }
+    CallOpts oa, oc;
+    int rc;
+    if ((rc = parse_opts(pa, syn_opts, oa)) || (rc = parse_opts(pc, ana_opts, oc))) return rc;
+    Plan* uniq[2] = {&pa, &pc};
+    std::sort(uniq, uniq + 2);
+    Plan** end = std::unique(uniq, uniq + 2);
+    for (Plan** q = uniq; q != end; ++q) (*q)->mu.lock();
+    struct Unlock { Plan** b; Plan** e; ~Unlock() { for (Plan** q = b; q != e; ++q) (*q)->mu.unlock(); } } unlock{uniq, end};
+    SHB_CUDA(cudaSetDevice(pc.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t per = (int64_t)pc.nlat * pc.nlon, n = per * batch;
+    if ((rc = grow_mul_grid(pc, n))) return rc;
+    double* g = pc.mul_grid;
+    if ((rc = do_synthesis(pa, batch, coef, cs_b, cs_nm, g, per, pc.nlon, 1, st, oa))) return rc;
+    k_mask_mul<<<(unsigned)((per + 255) / 256), 256, 0, st>>>(g, mask, pc.nlat, pc.nlon, ms_lat, ms_lon, per, batch);
+    return do_analysis(pc, batch, g, per, pc.nlon, 1, coef_out, os_b, os_nm, st, oc);
+}
 
 extern "C" int shb200_multiply(shb200_plan* syn_a, shb200_plan* syn_b, shb200_plan* ana, int32_t batch,
                                const double* coef_a, int64_t as_b, int64_t as_nm, const double* coef_b, int64_t bs_b, int64_t bs_nm,
@@ -38,12 +89,7 @@ extern "C" int shb200_multiply(shb200_plan* syn_a, shb200_plan* syn_b, shb200_pl
     const int64_t per = (int64_t)pc.nlat * pc.nlon, n = per * batch;
     // the two grids live in ONE buffer owned by the analysis plan (grown on demand; growing synchronises the device, so
     // no kernel of an earlier call can still be using the old allocation)
-    if (pc.mul_grid_elems < 2 * n) {
-        if (pc.mul_grid) { SHB_CUDA(cudaDeviceSynchronize()); cudaFree(pc.mul_grid); }
-        pc.mul_grid = nullptr; pc.mul_grid_elems = 0;
-        SHB_CUDA(cudaMalloc((void**)&pc.mul_grid, sizeof(double) * 2 * n));
-        pc.mul_grid_elems = 2 * n;
-    }
+    { int rcg = grow_mul_grid(pc, 2 * n); if (rcg) return rcg; }
     double* ga = pc.mul_grid;
     double* gb = pc.mul_grid + n;
     const CallOpts none;

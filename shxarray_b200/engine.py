@@ -561,6 +561,47 @@ class SHEngine:
         return out.cpu().numpy() if host else out
 
 
+    def apply_mask(self, coef, nmax, mask, lon, lat, nmax_out=None, quadrature="gauss", lat_weights=None, weight=None,
+                   syn_scale=None, ana_scale=None):
+        """Grid-space operator  analysis(mask x synthesis(coef))  with the grid kept on the device (shb200_apply_mask).
+
+        The sea-level equation's ocean function applied to a load: ``SpectralSeaLevelSolver.oceanf(load)``
+        (spectralsealevel.py:97-104) multiplies by an O(nsh^2) product-to-sum matrix that only exists for nmax <= 150
+        (:23-24); here the load is synthesised on ``lon`` x ``lat``, multiplied pointwise by the ocean mask and analysed
+        back -- any nmax, O(N^3), nothing but coefficients crosses PCIe.  ``syn_scale`` / ``ana_scale``: per-degree
+        factors fused into the two transforms (geoid / uplift kernels of ``load_earth``, :106-109).
+        coef [B, (nmax+1)^2] (numpy or torch CUDA); mask [nlat, nlon] (numpy or torch CUDA; uploaded once per call when
+        numpy -- keep it as a CUDA tensor across SLE iterations).  Returns [B, (nmax_out+1)^2]."""
+        import torch
+        nmax = int(nmax)
+        nmax_out = nmax if nmax_out is None else int(nmax_out)
+        lon = np.ascontiguousarray(lon, dtype=np.float64)
+        lat = np.ascontiguousarray(lat, dtype=np.float64)
+        host = not _is_torch(coef)
+        dev = torch.device("cuda", self.device)
+        tc = torch.as_tensor(np.ascontiguousarray(coef, dtype=np.float64), device=dev) if host else coef
+        tm = torch.as_tensor(np.ascontiguousarray(mask, dtype=np.float64), device=dev) if not _is_torch(mask) else mask
+        if tc.ndim == 1:
+            tc = tc[None]
+        if tuple(tm.shape) != (len(lat), len(lon)):
+            raise ValueError("apply_mask: mask must be [nlat, nlon]")
+        if tc.shape[1] != (nmax + 1) ** 2:
+            raise ValueError("apply_mask: coef must hold the full triangle of nmax")
+        B = tc.shape[0]
+        n, m = _nm_index_cached(nmax, 0)
+        pc = self._analysis_plan(nmax_out, lon, lat, B, quadrature, lat_weights, weight, None)
+        pa = self.get_plan(nmax, lat, lon, B, n=n, m=m)
+        out = torch.empty((B, (nmax_out + 1) ** 2), dtype=torch.float64, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        step = min(pa.max_batch, pc.max_batch)
+        for b0 in range(0, B, step):
+            nb = min(step, B - b0)
+            pa.apply_mask_dev(pc, nb, tc[b0].data_ptr(), tc.stride(0), tc.stride(1), tm.data_ptr(), tm.stride(0), tm.stride(1),
+                              out[b0].data_ptr(), out.stride(0), out.stride(1), stream, syn_scale=syn_scale, ana_scale=ana_scale)
+            self.launches += pa.info.launches_synthesis + pc.info.launches_analysis + 1
+        return out.cpu().numpy() if host else out
+
+
 _default = {}
 
 

@@ -203,6 +203,37 @@ class B200Backend(SHComputeBackendBase):
         daout.attrs["comments"] = self._credits
         return daout
 
+    # ------------------------------------------------------------------------------------------
+    def apply_mask(self, dash, damask, nmax_out=None, quadrature=None, syn_scale=None, ana_scale=None):
+        """Grid-space ocean-function operator: ``analysis(damask x synthesis(dash))`` with the grid kept on the device
+        (SHEngine.apply_mask).  Replaces ``SpectralSeaLevelSolver.oceanf(load)`` (spectralsealevel.py:97-104: a product-to-sum
+        matrix that exists for nmax <= 150 only).  damask: DataArray on a lon/lat grid (e.g. the ocean function rasterised on
+        ``lonlat_grid(nmax)``); dash: full-triangle SH DataArray."""
+        loninfo = find_lon(damask.coords)
+        latinfo = find_lat(damask.coords)
+        gtype = loninfo.var.attrs.get("shxarray_gtype", None)
+        if quadrature is None:
+            quadrature = "gauss" if gtype == "gauss" else "shlib"
+        lon = np.asarray(loninfo.var.data, dtype=np.float64)
+        lat = np.asarray(latinfo.var.data, dtype=np.float64)
+        mask = np.asarray(damask.transpose(latinfo.var.dims[0], loninfo.var.dims[0]).data, dtype=np.float64)
+        nmax = int(dash.sh.nmax)
+        nmax_out = nmax if nmax_out is None else int(nmax_out)
+        dast, auxdim = _stack_aux(dash, ["nm"])
+        dast = dast.transpose(auxdim, "nm")
+        n = dast.nm.n.data.astype(np.int64)
+        m = dast.nm.m.data.astype(np.int64)
+        full = np.zeros((dast.sizes[auxdim], (nmax + 1) ** 2))
+        full[:, n * n + n + m] = np.asarray(dast.data, dtype=np.float64)
+        out = self._engine.apply_mask(full, nmax, mask, lon, lat, nmax_out=nmax_out, quadrature=quadrature, syn_scale=syn_scale, ana_scale=ana_scale)
+        coords = {auxdim: dast.coords[auxdim], SHindexBase.name: SHindexBase.nm_mi(nmax_out, 0)}
+        daout = _unstack_aux(xr.DataArray(out, coords=coords, dims=[auxdim, SHindexBase.name]), auxdim)
+        daout.name = dash.name
+        daout.attrs.update(get_cfglobal())
+        daout.attrs["history"] = "Grid-space mask operator applied using b200 backend"
+        daout.attrs["comments"] = self._credits
+        return daout
+
     # ---- shlib-only extras (xr_accessor.py:36-51,203-207 default to engine="shlib" for these) ----------------------------
     def gaunt(self, *a, **k):
         self._notImplemented("gaunt")

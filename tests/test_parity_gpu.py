@@ -887,3 +887,32 @@ def test_latitude_shards_scatter_to_the_full_grid(engine, nmax, B, gtype):
     q = "gauss" if gtype == "gauss" else "shlib"
     a1 = engine.analysis(full, nmax, lon, lat, quadrature=q)
     assert torch.equal(sh.analysis_msharded(full, nmax, lon, lat, quadrature=q), a1)
+
+
+@pytest.mark.parametrize("nmax,B", [(48, 5), (96, 20)])
+def test_grid_space_mask_operator_vs_oracle(engine, nmax, B):
+    """shb200_apply_mask (the grid-space ocean function of the sea-level equation, replaces spectralsealevel.py:97-104):
+    analysis(mask x synthesis(load)) on the device against the same three steps done by the oracle; fused per-degree scales
+    equal scaling the coefficients on the host."""
+    import torch
+    lon, lat = O.shlib_grid(nmax)
+    n, m = O.nm_index(nmax)
+    rng = np.random.default_rng(5)
+    c = S.random_coefficients(nmax, B, kaula=False, seed=9)
+    yy, xx = np.meshgrid(lat, lon, indexing="ij")
+    mask = ((np.sin(3 * np.deg2rad(xx)) * np.cos(2 * np.deg2rad(yy)) + 0.2 * rng.standard_normal(xx.shape)) > 0).astype(np.float64)
+    f = np.moveaxis(O.synthesis(c, n, m, lon, lat, kind=O.best_kind(), nthreads=O.max_threads()), 2, 0)
+    ref = O.analysis(f * mask[None], nmax, lon, lat, kind=O.best_kind(), nthreads=O.max_threads())
+    got = engine.apply_mask(c, nmax, mask, lon, lat, quadrature="shlib")
+    assert per_field_err(got, ref) <= TOL
+    # device-resident operands, mask as a strided view, fused scales
+    s1 = np.linspace(1.0, 2.0, nmax + 1)
+    s2 = 1.0 / (1.0 + np.arange(nmax + 1.0))
+    big = torch.zeros((len(lat), 2 * len(lon)), dtype=torch.float64, device="cuda")
+    big[:, ::2] = torch.from_numpy(mask).cuda()
+    got2 = engine.apply_mask(torch.from_numpy(c).cuda(), nmax, big[:, ::2], lon, lat, quadrature="shlib", syn_scale=s1, ana_scale=s2)
+    ref2 = engine.analysis(engine.synthesis(c * s1[n][None, :], lon=lon, lat=lat, nmax=nmax) * mask[None], nmax, lon, lat) * s2[n][None, :]
+    assert per_field_err(got2.cpu().numpy(), ref2) <= 1e-14
+    # the ocean function itself (oceanf(None)) is the analysis of the mask; a unit load recovers it
+    unit = np.zeros((1, (nmax + 1) ** 2)); unit[0, 0] = 1.0
+    assert per_field_err(engine.apply_mask(unit, nmax, mask, lon, lat, quadrature="shlib"), engine.analysis(mask[None], nmax, lon, lat)) <= 1e-14
