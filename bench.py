@@ -297,14 +297,20 @@ def main():
     kernels = plan.last_kernels()          # of the last device-resident analysis call
     L_rows = plan.info.nrows
     paired = L_rows < NLAT
-    flops_leg = (1.0 if paired else 2.0) * nsh * NLAT * BATCH          # F_sym / F_alg Legendre term x batch
+    flops_full = (1.0 if paired else 2.0) * nsh * NLAT * BATCH         # F_sym / F_alg Legendre term x batch
+    # executed work only (never credit skipped work): the table kernels do not visit (n, m, row) triples with
+    # |P_nm| < 1e-24 (polar skipping); the library reports the fraction each direction visits
+    visited = {"syn_legendre": plan.info.legendre_visited_synthesis, "ana_legendre": plan.info.legendre_visited_analysis}
     dom = "syn_legendre" if acc["syn_legendre"] >= acc["ana_legendre"] else "ana_legendre"
+    flops_leg = flops_full * visited[dom]
     peak, peak_src = fp64_peak_tflops()
     achieved = flops_leg / (acc[dom] * 1e-3) * 1e-12
     kname = {"syn_legendre": "k_leg_syn_tab", "ana_legendre": "k_leg_ana_tab"}[dom] if plan.info.dmma == 2 else None
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(kname) if kname else None, "traffic_unit": "bytes per launch (dram read+write, ncu)", "flops_per_launch": flops_leg, "ms_per_launch": acc[dom], "peak_source": peak_src,
                 "symmetry": "mirror-latitude pairing used: F_sym = nsh*L per field" if paired else "no pairing: F_alg = 2*nsh*L per field",
+                "executed_fraction": visited, "flops_per_launch_unskipped": flops_full,
+                "executed_note": "flops_per_launch counts EXECUTED work: F_sym x the fraction of (n,m,row) triples the kernel visits (|P_nm| < 1e-24 towards the poles is skipped)",
                 "stages_ms": acc}
 
     # ---- FP64 peak re-measured on this box: cuBLAS DGEMM 8192^3 through torch (a library GEMM as yardstick only) --------
@@ -323,7 +329,7 @@ def main():
         return 3 * 2.0 * n ** 3 / (t0_.elapsed_time(t1_) * 1e-3) * 1e-12
 
     dgemm = dgemm_tflops()
-    flops_step = 2.0 * flops_leg + 2.0 * 2.5 * NLAT * NLON * np.log2(NLON) * BATCH     # both directions: Legendre (F_sym) + FFT terms
+    flops_step = flops_full * (visited["syn_legendre"] + visited["ana_legendre"]) + 2.0 * 2.5 * NLAT * NLON * np.log2(NLON) * BATCH     # both directions: executed Legendre work + FFT terms
     roofline["fp64_peak_check"] = {"cublas_dgemm_8192_tflops": dgemm, "frac_vs_dgemm": achieved / dgemm,
                                    "note": "cuBLAS DGEMM measured in this run; `peak` is the DMMA issue-rate microbenchmark (tools/fp64_peaks.cu)"}
     roofline["whole_step"] = {"flops_per_step": flops_step, "achieved_tflops": flops_step / (ms_total / args.steps * 1e-3) * 1e-12,

@@ -43,7 +43,9 @@ enum { SHB200_FLAG_NO_SYMMETRY = 1, /* do not pair mirror latitudes */
        SHB200_FLAG_DENSE_LON = 2,   /* force the dense trig longitude stage (no FFT) */
        SHB200_FLAG_NO_DMMA = 4,     /* force the CUDA-core (DFMA) Legendre kernels */
        SHB200_FLAG_TIMING = 8,      /* record CUDA events around every stage (see shb200_plan_stage_times) */
-       SHB200_FLAG_NO_PTABLE = 16   /* never keep a device-resident P_nm table: fused on-the-fly recursion kernels */ };
+       SHB200_FLAG_NO_PTABLE = 16,  /* never keep a device-resident P_nm table: fused on-the-fly recursion kernels */
+       SHB200_FLAG_NO_POLAR_SKIP = 32 /* table kernels visit every (n, m, latitude) triple, also where |P_nm| < 1e-24 (see
+                                         shb200_plan_info.legendre_visited_*) */ };
 
 typedef struct shb200_plan shb200_plan;
 
@@ -77,6 +79,13 @@ typedef struct shb200_plan_info {
     int64_t workspace_bytes;     /* device memory owned by the plan */
     int32_t launches_synthesis;  /* kernels launched per synthesis call */
     int32_t launches_analysis;   /* kernels launched per analysis call */
+    /* Fraction of the (degree, order, latitude-row) triples the Legendre stage of a full-width call actually visits.  The
+     * table kernels skip, per order and 32-row tile, the leading 16-degree blocks in which every |P_nm| < 1e-24 (towards
+     * the poles P_nm ~ sin^m(theta) stays negligible until n ~ m/sin(theta): the "polar optimisation" of SHTns); a term that
+     * small changes no result above 1e-12 of the field maximum.  1.0 for the other kernel families / with
+     * SHB200_FLAG_NO_POLAR_SKIP.  Roofline figures must count executed work only: F_sym x this fraction. */
+    double legendre_visited_synthesis;
+    double legendre_visited_analysis;
 } shb200_plan_info;
 
 /* Per-call options of the four transform entry points (NULL = defaults).  Nothing a call changes is kept on the plan:

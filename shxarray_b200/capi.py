@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libshb200.so")
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
 MODE_GRID, MODE_POINTS = 0, 1
 QUAD_NONE, QUAD_SHLIB, QUAD_LATWEIGHTS = 0, 1, 2
-FLAG_NO_SYMMETRY, FLAG_DENSE_LON, FLAG_NO_DMMA, FLAG_TIMING, FLAG_NO_PTABLE = 1, 2, 4, 8, 16
+FLAG_NO_SYMMETRY, FLAG_DENSE_LON, FLAG_NO_DMMA, FLAG_TIMING, FLAG_NO_PTABLE, FLAG_NO_POLAR_SKIP = 1, 2, 4, 8, 16, 32
 
 # every symbol declared in include/shb200.h
 EXPORTS = [
@@ -46,6 +46,7 @@ class PlanInfo(C.Structure):
         ("lon_fft", C.c_int32), ("dmma", C.c_int32),
         ("nsh", C.c_int64), ("nsh_full", C.c_int64), ("workspace_bytes", C.c_int64),
         ("launches_synthesis", C.c_int32), ("launches_analysis", C.c_int32),
+        ("legendre_visited_synthesis", C.c_double), ("legendre_visited_analysis", C.c_double),
     ]
 
 

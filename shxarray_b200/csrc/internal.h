@@ -52,7 +52,10 @@ struct DevTables {
     int m0, mstride;         // analysis order shard: this plan integrates orders m = m0 + i*mstride only (multi-GPU m-sharding)
     const int64_t* pt_base;  // [nmax+2] first 16-degree block of each order in the tiled P table
     int RT32;                // row tiles (of 32) in the P table = Rpad/32
+    const int* first_blk;    // [(nmax+1)*RT32] polar skipping: first 16-degree block of order m in which some |P_nm| of the 32-row
+                             // tile reaches POLAR_EPS (blocks before it are not visited); null = visit everything
 };
+constexpr double POLAR_EPS = 1e-24;
 
 // Column of (cos/sin cs, field b) inside a Cm / G row: fields come in groups of GS with the cosine and sine part of a
 // group adjacent, [b/GS][cs][b%GS], so that the longitude stage (GS fields per CTA) touches full 128-byte lines.
@@ -107,6 +110,10 @@ struct Plan {
     double* G = nullptr;    // [(nmax+1)][nrows][2][Gs] (+64 slack rows)
     double* Ptab = nullptr; // tiled device-resident P_nm table (legendre_tab.cu) or null
     int Rpad = 0;
+    // polar skipping (table kernels): tile lists of the persistent synthesis kernel, heaviest tile first, for its three tile
+    // shapes (32 * {2, 4, 8} rows); fraction of the (n, m, row) triples visited per shape (synthesis) / stage width (analysis)
+    const int2* syn_order[3] = {nullptr, nullptr, nullptr};   // (tile, first chunk) per list position
+    double visited_syn[3] = {1.0, 1.0, 1.0}, visited_ana[3] = {1.0, 1.0, 1.0};
     // duplicates in the nm list (rare; Ynm.hpp accepts them, dgemv sums them)
     int64_t ndup = 0;
     const int64_t* dup_slot = nullptr;  // device [ndup] slot*2+cs

@@ -31,7 +31,8 @@ constexpr int PT_SUB = 16 * 34;      // doubles per [16 degrees][32 rows + 2] su
 
 // ------------------------------------------------------------------------------------------------
 // table generation: thread <-> (row, order); a warp writes 32 consecutive rows of one sub-tile row (256 B)
-__global__ void __launch_bounds__(128) k_ptab_gen(DevTables t, double* __restrict__ Ptab) {
+// first_k (optional): per (order, 32-row tile) the smallest degree offset n - m at which some row of the tile has |P_nm| >= POLAR_EPS
+__global__ void __launch_bounds__(128) k_ptab_gen(DevTables t, double* __restrict__ Ptab, int* __restrict__ first_k) {
     const int m = blockIdx.y;
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     const int N = t.nmax, R = t.nrows;
@@ -43,12 +44,18 @@ __global__ void __launch_bounds__(128) k_ptab_gen(DevTables t, double* __restric
     const double* __restrict__ w = t.wnm + tmm;
     const double* __restrict__ ri = t.rinv + tmm;
     double* base = Ptab + (t.pt_base[m] * t.RT32 + (row >> 5)) * PT_SUB + (row & 31);
-    for (int k = 0; k <= N - m; ++k) base[(int64_t)(k >> 4) * t.RT32 * PT_SUB + (k & 15) * 34] = rec.next(w, ri, pmm);
+    int kfirst = 0x7f7f7f7f;
+    for (int k = 0; k <= N - m; ++k) {
+        const double v = rec.next(w, ri, pmm);
+        base[(int64_t)(k >> 4) * t.RT32 * PT_SUB + (k & 15) * 34] = v;
+        if (kfirst == 0x7f7f7f7f && fabs(v) >= POLAR_EPS) kfirst = k;
+    }
+    if (first_k && kfirst != 0x7f7f7f7f) atomicMin(&first_k[m * t.RT32 + (row >> 5)], kfirst);
 }
 
-void launch_ptab_gen(const Plan& p, cudaStream_t st) {
+void launch_ptab_gen(const Plan& p, int* first_k, cudaStream_t st) {
     dim3 grid((p.nrows + 127) / 128, p.nmax + 1);
-    k_ptab_gen<<<grid, 128, 0, st>>>(p.t, p.Ptab);
+    k_ptab_gen<<<grid, 128, 0, st>>>(p.t, p.Ptab, first_k);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -72,7 +79,7 @@ struct TS {
 // warp keeps filling the ring across tile boundaries, so the tensor pipe does not drain 29 times per SM per launch.
 template <int NWC>
 __global__ void __launch_bounds__(TS<NWC>::NTHREADS, 1) k_leg_syn_tab(DevTables t, const double* __restrict__ Ptab, const double* __restrict__ Cm,
-                                                                       double* __restrict__ G, int nrt, int ntiles) {
+                                                                       double* __restrict__ G, int nrt, int ntiles, const int2* __restrict__ order) {
     using C_ = TS<NWC>;
     constexpr int NWR = C_::NWR, TR = C_::TR, CH = C_::CH, NCOLS = C_::NCOLS, CROW = C_::CROW, STAGES = C_::STAGES, NCONS = C_::NCONS, NTHREADS = C_::NTHREADS;
     extern __shared__ __align__(128) unsigned char smraw[];
@@ -102,15 +109,17 @@ __global__ void __launch_bounds__(TS<NWC>::NTHREADS, 1) k_leg_syn_tab(DevTables 
         // ------------------------------------------------------------------ TMA warp
         int gc = 0;                                     // chunks issued so far (ring position)
         for (int rnd = 0;; ++rnd) {
-            const int tile = rnd * P + ((rnd & 1) ? P - 1 - c : c);
-            if (tile >= ntiles) { if (rnd * P >= ntiles) break; else continue; }
+            const int ti = rnd * P + ((rnd & 1) ? P - 1 - c : c);
+            if (ti >= ntiles) { if (rnd * P >= ntiles) break; else continue; }
+            const int2 td = order ? __ldg(&order[ti]) : make_int2(ti, 0);
+            const int tile = td.x, ch0 = td.y;
             const int m = tile / nrt, rt = tile - m * nrt;
             const int nchunks = (N - m + CH) / CH;
             const int64_t tmm = tri(m, m, N);
             // sub-tiles past the last row tile of the order belong to the next degree block (or the slack behind the
             // table): fetched with the rest, never used
             const double* psrc = Ptab + (t.pt_base[m] * t.RT32 + NWR * rt) * PT_SUB;
-            for (int ch = 0; ch < nchunks; ++ch, ++gc) {
+            for (int ch = ch0; ch < nchunks; ++ch, ++gc) {
                 const int s = gc % STAGES;
                 mbar_wait(&empty[s], ((gc / STAGES) & 1) ^ 1);
                 const int k0 = ch * CH;
@@ -138,9 +147,19 @@ __global__ void __launch_bounds__(TS<NWC>::NTHREADS, 1) k_leg_syn_tab(DevTables 
         const int lr = lane >> 2, lk = lane & 3;
         int gc = 0;
         int prev = -1;      // stage whose fragments were consumed last; released only after the NEXT stage has been acquired
+        // tile descriptors are fetched one round ahead: the load of round rnd + 1 is in flight while round rnd is computed
+        auto tile_of = [&](int rnd) { return rnd * P + ((rnd & 1) ? P - 1 - c : c); };
+        auto fetch = [&](int rnd) {
+            const int ti = tile_of(rnd);
+            return (order && ti < ntiles) ? __ldg(&order[ti]) : make_int2(ti, 0);
+        };
+        int2 td_next = fetch(0);
         for (int rnd = 0;; ++rnd) {
-            const int tile = rnd * P + ((rnd & 1) ? P - 1 - c : c);
-            if (tile >= ntiles) { if (rnd * P >= ntiles) break; else continue; }
+            const int ti = tile_of(rnd);
+            const int2 td = td_next;
+            td_next = fetch(rnd + 1);
+            if (ti >= ntiles) { if (rnd * P >= ntiles) break; else continue; }
+            const int tile = td.x, ch0 = td.y;
             const int m = tile / nrt, rt = tile - m * nrt;
             const int nchunks = (N - m + CH) / CH;
             const int row0 = rt * TR;
@@ -152,7 +171,7 @@ __global__ void __launch_bounds__(TS<NWC>::NTHREADS, 1) k_leg_syn_tab(DevTables 
                 for (int g = 0; g < 4; ++g)
 #pragma unroll
                     for (int cb = 0; cb < 4; ++cb) { acc[e][g][cb][0] = 0.0; acc[e][g][cb][1] = 0.0; }
-            for (int ch = 0; ch < nchunks; ++ch, ++gc) {
+            for (int ch = ch0; ch < nchunks; ++ch, ++gc) {
                 const int s = gc % STAGES;
                 mbar_wait(&full[s], (gc / STAGES) & 1);
                 // Release of the previous stage is deferred to here: ptxas is free to schedule an mbarrier arrive ahead of
@@ -246,6 +265,11 @@ __global__ void __launch_bounds__(TA<NCQ>::NTHREADS, 1) k_leg_ana_tab(DevTables 
         for (int g = 0; g < 2; ++g) { mbar_init(&gfull[g], 1); mbar_init(&gempty[g], NCONS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // Polar skipping: s0[rt] = first stage (NS degrees) of this order that row tile rt has to visit; the stages before it hold
+    // only |P_nm| < POLAR_EPS for its 32 rows.  Producer and consumers derive the same schedule from it: a (super-block, row
+    // tile) pair whose stages all lie before s0[rt] is not visited at all (no G tile is fetched for it).
+    __shared__ int s0_s[256];                          // plans have at most 8192 rows (plan.cu)
+    for (int rt = tid; rt < nrt; rt += C_::NTHREADS) s0_s[rt] = t.first_blk ? t.first_blk[m * t.RT32 + rt] / (2 * NDG) : 0;
     __syncthreads();
 
     // Register reallocation: compiled for 168 registers per thread (12 warps), the accumulators alone take 128 of them and
@@ -257,13 +281,15 @@ __global__ void __launch_bounds__(TA<NCQ>::NTHREADS, 1) k_leg_ana_tab(DevTables 
         if (warp > NCONS / 32) return;
         // ------------------------------------------------------------------ TMA warp
         const double* pbase = Ptab + t.pt_base[m] * t.RT32 * PT_SUB;
-        int sidx = 0;
+        int sidx = 0, it = 0;
         for (int sb = 0; sb < nsb; ++sb) {
             const int ninner = min(SB / NS, (N - m - sb * SB + NS) / NS);     // stages of this super-block that hold degrees <= nmax
             for (int rt = 0; rt < nrt; ++rt) {
-                const int it = sb * nrt + rt;
+                const int in0 = max(0, s0_s[rt] - sb * (SB / NS));
+                if (in0 >= ninner) continue;
                 const int gb = it & 1;
                 mbar_wait(&gempty[gb], ((it >> 1) & 1) ^ 1);
+                ++it;
                 {
                     const int nr = min(RT, R - rt * RT);
                     if (lane == 0) mbar_arrive_expect_tx(&gfull[gb], (uint32_t)(nr * 2 * ncols * 8));
@@ -274,7 +300,7 @@ __global__ void __launch_bounds__(TA<NCQ>::NTHREADS, 1) k_leg_ana_tab(DevTables 
                         bulk_g2s(&gt[gb * C_::GSZ + (lane * 2 + 1) * grow], src + t.Gs, (uint32_t)(ncols * 8), &gfull[gb]);
                     }
                 }
-                for (int inner = 0; inner < ninner; ++inner, ++sidx) {
+                for (int inner = in0; inner < ninner; ++inner, ++sidx) {
                     const int s = sidx % PSTAGES;
                     mbar_wait(&pempty[s], ((sidx / PSTAGES) & 1) ^ 1);
                     const int k0 = sb * SB + inner * NS;
@@ -293,7 +319,7 @@ __global__ void __launch_bounds__(TA<NCQ>::NTHREADS, 1) k_leg_ana_tab(DevTables 
         const int e = warp & 1, cq = (warp >> 1) % NCQ, dg = (warp >> 1) / NCQ;
         const int lr = lane >> 2, lk = lane & 3;
         double acc[2 * C_::SPB][4][2];
-        int sidx = 0;
+        int sidx = 0, it = 0;
         int prev_s = -1, prev_g = -1;   // P stage / G buffer consumed last: released after the next one has been acquired (see k_leg_syn_tab)
         for (int sb = 0; sb < nsb; ++sb) {
             const int ninner = min(SB / NS, (N - m - sb * SB + NS) / NS);
@@ -302,16 +328,19 @@ __global__ void __launch_bounds__(TA<NCQ>::NTHREADS, 1) k_leg_ana_tab(DevTables 
 #pragma unroll
                 for (int cb = 0; cb < 4; ++cb) { acc[nb][cb][0] = 0.0; acc[nb][cb][1] = 0.0; }
             for (int rt = 0; rt < nrt; ++rt) {
-                const int it = sb * nrt + rt;
+                const int in0 = max(0, s0_s[rt] - sb * (SB / NS));
+                if (in0 >= ninner) continue;
                 const int gb = it & 1;
                 const int nr = min(RT, R - rt * RT);
                 mbar_wait(&gfull[gb], (it >> 1) & 1);
+                ++it;
                 if (prev_g >= 0) { __syncwarp(); if (lane == 0) mbar_arrive(&gempty[prev_g]); }
                 prev_g = gb;
                 const double* __restrict__ GT = gt + gb * C_::GSZ + e * grow + 32 * cq + lr;
 #pragma unroll
                 for (int inner = 0; inner < SB / NS; ++inner) {
                     if (inner >= ninner) break;
+                    if (inner < in0) continue;
                     const int s = sidx % PSTAGES;
                     mbar_wait(&pfull[s], (sidx / PSTAGES) & 1);
                     ++sidx;
@@ -373,7 +402,8 @@ static bool launch_syn_tab_nwc(const Plan& p, cudaStream_t st) {
     const int ncolt = (p.NC + C_::NCOLS - 1) / C_::NCOLS;
     dim3 grid(std::max(1, std::min(ntiles, sms / std::min(ncolt, sms))), ncolt);
     trace_kernel(p, NWC == 4 ? "k_leg_syn_tab<4>" : (NWC == 2 ? "k_leg_syn_tab<2>" : "k_leg_syn_tab<1>"));
-    k_leg_syn_tab<NWC><<<grid, C_::NTHREADS, C_::SMEM, st>>>(p.t, p.Ptab, p.Cm, p.G, nrt, ntiles);
+    const int2* order = p.t.first_blk ? p.syn_order[NWC == 4 ? 0 : (NWC == 2 ? 1 : 2)] : nullptr;
+    k_leg_syn_tab<NWC><<<grid, C_::NTHREADS, C_::SMEM, st>>>(p.t, p.Ptab, p.Cm, p.G, nrt, ntiles, order);
     return true;
 }
 

@@ -8,6 +8,7 @@
 //   sectorial products (1e280 scaling)   Legendre_nm.hpp:101,127-130
 //   alpha = weight*cos(lat*(pi/180))     analysis.pyx:121,129
 // and decides the execution plan: mirror-latitude pairing, FFT vs dense longitude stage, kernel family.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -47,9 +48,62 @@ static int dev_alloc(Plan& p, size_t bytes, void** out) {
     return 0;
 }
 
-void launch_ptab_gen(const Plan& p, cudaStream_t st);
+void launch_ptab_gen(const Plan& p, int* first_k, cudaStream_t st);
 
 static double ulp_scale(double x) { return std::ldexp(1.0, -52) * std::fmax(std::fabs(x), 1.0); }
+
+// Polar skipping (legendre_tab.cu): turn the per-(order, 32-row tile) first significant degree offsets into first 16-degree
+// blocks (in place, on the device array the kernels read), the heaviest-first tile lists of the persistent synthesis kernel
+// and the fractions of the (n, m, row) triples each kernel shape still visits.
+static int build_polar_schedule(Plan& p, int* first_k_dev) {
+    DevTables& t = p.t;
+    const int N = p.nmax, R = p.nrows, RT32 = t.RT32;
+    std::vector<int> fb((size_t)(N + 1) * RT32);
+    SHB_CUDA(cudaMemcpy(fb.data(), first_k_dev, sizeof(int) * fb.size(), cudaMemcpyDeviceToHost));
+    for (int m = 0; m <= N; ++m) {
+        const int nblk = (N - m + 16) / 16;
+        for (int q = 0; q < RT32; ++q) {
+            int& v = fb[(size_t)m * RT32 + q];
+            v = std::min(v / 16, nblk);            // untouched entries (0x7f7f7f7f: pad rows, all-negligible tiles) -> nblk
+        }
+    }
+    SHB_CUDA(cudaMemcpy(first_k_dev, fb.data(), sizeof(int) * fb.size(), cudaMemcpyHostToDevice));
+    t.first_blk = first_k_dev;
+    const double all = (double)tri_size(N) * R;
+    auto rows_in = [&](int q) { return std::max(0, std::min(32, R - 32 * q)); };
+    for (int v = 0; v < 3; ++v) {
+        // synthesis tile shapes: NWC = 4, 2, 1 -> 2, 4, 8 sub-tiles of 32 rows (legendre_tab.cu: TS<NWC>)
+        const int nwr = 2 << v, nrt = (R + 32 * nwr - 1) / (32 * nwr);
+        std::vector<std::pair<int, int>> work((size_t)(N + 1) * nrt);
+        double visited = 0.0;
+        for (int m = 0; m <= N; ++m) {
+            const int nblk = (N - m + 16) / 16;
+            for (int rt = 0; rt < nrt; ++rt) {
+                int f = nblk, rows = 0;
+                for (int q = nwr * rt; q < std::min(RT32, nwr * (rt + 1)); ++q) { f = std::min(f, fb[(size_t)m * RT32 + q]); rows += rows_in(q); }
+                work[(size_t)m * nrt + rt] = {nblk - f, m * nrt + rt};
+                visited += (double)std::max(0, N - m + 1 - 16 * f) * rows;
+            }
+        }
+        std::stable_sort(work.begin(), work.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first > b.first; });
+        // descriptor per list position: (tile = m * nrt + rt, first chunk to visit) -- one load per tile in the kernel
+        std::vector<int2> order(work.size());
+        for (size_t i = 0; i < work.size(); ++i) {
+            const int tile = work[i].second, m = tile / nrt;
+            order[i] = make_int2(tile, (N - m + 16) / 16 - work[i].first);
+        }
+        int rc = upload(p, order, &p.syn_order[v]);
+        if (rc) return rc;
+        p.visited_syn[v] = visited / all;
+        // analysis stage widths: NCQ = 4, 2, 1 -> stages of 2, 4, 8 blocks (legendre_tab.cu: TA<NCQ>), row tiles of 32
+        const int sblk = 2 << v;
+        visited = 0.0;
+        for (int m = 0; m <= N; ++m)
+            for (int q = 0; q < RT32; ++q) visited += (double)std::max(0, N - m + 1 - 16 * sblk * (fb[(size_t)m * RT32 + q] / sblk)) * rows_in(q);
+        p.visited_ana[v] = visited / all;
+    }
+    return 0;
+}
 
 static int build_plan(const shb200_plan_desc& d, Plan& p) {
     if (d.nmax < 0 || d.max_batch < 1 || d.nlat < 1 || d.nlon < 1 || !d.lat_deg || !d.lon_deg) {
@@ -158,6 +212,16 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
             i1.push_back(i); i2.push_back(mate);
         }
     }
+    // rows from the poles to the equator (stable in the caller's order among equal |cos(theta)|): a 32-row tile of the table
+    // kernels then spans one latitude band, which is what makes polar skipping (first_blk) effective for any latitude order
+    {
+        std::vector<int> ord(i1.size());
+        for (size_t r = 0; r < ord.size(); ++r) ord[r] = (int)r;
+        std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return fabs(cost_lat[i1[a]]) > fabs(cost_lat[i1[b]]); });
+        std::vector<int> a1(i1.size()), a2(i1.size());
+        for (size_t r = 0; r < ord.size(); ++r) { a1[r] = i1[ord[r]]; a2[r] = i2[ord[r]]; }
+        i1.swap(a1); i2.swap(a2);
+    }
     p.nrows = (int)i1.size();
     const int R = p.nrows;
     if (d.quadrature != SHB200_QUAD_NONE && R > 8192) {
@@ -260,7 +324,7 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
         p.dscale[w] = (double*)q;
     }
     t.nmax = N; t.nrows = R; t.nlat = d.nlat; t.nlon = d.nlon; t.Bp = p.Bp; t.NC = p.NC; t.GS = p.Bp >= 8 ? 8 : 4;
-    t.Cs = p.NC + 2; t.Gs = p.NC; t.pt_base = nullptr; t.RT32 = 0; t.m0 = 0; t.mstride = 1;
+    t.Cs = p.NC + 2; t.Gs = p.NC; t.pt_base = nullptr; t.RT32 = 0; t.m0 = 0; t.mstride = 1; t.first_blk = nullptr;
 
     void* ptr;
     // 16 / 64 slack rows: the tensor-core kernels fetch whole 16-degree / 32-row blocks, also past the last order
@@ -300,8 +364,16 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
                 p.workspace_bytes += sizeof(double) * pt_elems;
                 p.Ptab = (double*)tab;
                 SHB_CUDA(cudaMemset(p.Ptab, 0, sizeof(double) * pt_elems));
-                launch_ptab_gen(p, 0);
+                int* first_k = nullptr;      // per (order, 32-row tile): first degree offset n - m with |P_nm| >= POLAR_EPS
+                const size_t nfk = (size_t)(N + 1) * t.RT32;
+                if (!(d.flags & SHB200_FLAG_NO_POLAR_SKIP)) {
+                    if ((rc = dev_alloc(p, sizeof(int) * nfk, &ptr))) return rc;
+                    first_k = (int*)ptr;
+                    SHB_CUDA(cudaMemset(first_k, 0x7f, sizeof(int) * nfk));
+                }
+                launch_ptab_gen(p, first_k, 0);
                 SHB_CUDA(cudaDeviceSynchronize());
+                if (first_k && (rc = build_polar_schedule(p, first_k))) return rc;
             } else {
                 cudaGetLastError();      // clear the allocation error
                 t.RT32 = 0;
@@ -475,6 +547,9 @@ int shb200_plan_get_info(const shb200_plan* plan, shb200_plan_info* info) {
     info->nsh = p.nsh; info->nsh_full = (int64_t)(p.nmax + 1) * (p.nmax + 1);
     info->workspace_bytes = p.workspace_bytes;
     info->launches_synthesis = p.launches_syn; info->launches_analysis = p.launches_ana;
+    const int shape = p.NC > 64 ? 0 : (p.NC > 32 ? 1 : 2);      // tile shape of a full-width call (legendre_tab.cu)
+    info->legendre_visited_synthesis = p.Ptab && p.t.first_blk ? p.visited_syn[shape] : 1.0;
+    info->legendre_visited_analysis = p.Ptab && p.t.first_blk ? p.visited_ana[shape] : 1.0;
     return 0;
 }
 

@@ -916,3 +916,41 @@ def test_grid_space_mask_operator_vs_oracle(engine, nmax, B):
     # the ocean function itself (oceanf(None)) is the analysis of the mask; a unit load recovers it
     unit = np.zeros((1, (nmax + 1) ** 2)); unit[0, 0] = 1.0
     assert per_field_err(engine.apply_mask(unit, nmax, mask, lon, lat, quadrature="shlib"), engine.analysis(mask[None], nmax, lon, lat)) <= 1e-14
+
+
+@pytest.mark.parametrize("nmax,B,gtype", [(200, 40, "gauss"), (300, 64, "regular"), (128, 16, "gauss")])
+def test_polar_skipping_changes_nothing_above_1e_minus_13(nmax, B, gtype):
+    """Table kernels skip (n, m, row) triples with |P_nm| < 1e-24 (the leading degree blocks of an order towards the poles).
+    Against the same kernels visiting everything (SHB200_FLAG_NO_POLAR_SKIP) the results agree far below the 1e-12
+    contract, the visited fraction is reported, and shuffled latitudes skip as much as sorted ones."""
+    import torch
+    g = sb.lonlat_grid(nmax, gtype=gtype)
+    lon, lat = g["lon"], g["lat"]
+    c = torch.from_numpy(S.random_coefficients(nmax, B, kaula=False, seed=123)).cuda()
+    q = dict(quadrature=capi.QUAD_LATWEIGHTS, weight=1.0 / (2 * len(lon)), lat_weights=g["lat_weights"]) if gtype == "gauss" else \
+        dict(quadrature=capi.QUAD_SHLIB, weight=float(sb.analysis_weight_shlib(lon, lat)))
+    nsh = (nmax + 1) ** 2
+    res = {}
+    perm = np.random.default_rng(1).permutation(len(lat))
+    for tag, flags, la, extra in (("skip", 0, lat, q), ("all", capi.FLAG_NO_POLAR_SKIP, lat, q),
+                                  ("shuffled", 0, lat[perm], dict(q, lat_weights=g["lat_weights"][perm]) if gtype == "gauss" else q)):
+        plan = capi.Plan(nmax, la, lon, max_batch=B, flags=flags, **extra)
+        assert plan.info.dmma == 2
+        f = torch.empty((B, len(lat), len(lon)), dtype=torch.float64, device="cuda")
+        a = torch.empty((B, nsh), dtype=torch.float64, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        plan.synthesis_dev(B, c.data_ptr(), nsh, 1, f.data_ptr(), f.stride(0), f.stride(1), 1, st)
+        plan.analysis_dev(B, f.data_ptr(), f.stride(0), f.stride(1), 1, a.data_ptr(), nsh, 1, st)
+        torch.cuda.synchronize()
+        res[tag] = (f.cpu().numpy(), a.cpu().numpy(), plan.info.legendre_visited_synthesis, plan.info.legendre_visited_analysis)
+        plan.close()
+    assert res["all"][2] == 1.0 and res["all"][3] == 1.0
+    # tile granularity decides how much is skipped: 32-row tiles x 32-degree stages (analysis), 64-row tiles (synthesis)
+    assert 0.5 < res["skip"][2] <= 1.0 and 0.5 < res["skip"][3] <= 1.0
+    if nmax == 300:
+        assert res["skip"][2] < 0.92 and res["skip"][3] < 0.9
+    assert abs(res["shuffled"][2] - res["skip"][2]) < 1e-12 and abs(res["shuffled"][3] - res["skip"][3]) < 1e-12
+    assert per_field_err(res["skip"][0], res["all"][0]) <= 1e-13
+    assert per_field_err(res["skip"][1], res["all"][1]) <= 1e-13
+    inv = np.argsort(perm)
+    assert per_field_err(res["shuffled"][0][:, inv, :], res["all"][0]) <= 1e-13

@@ -74,4 +74,4 @@ if __name__ == "__main__":
     add("cfg4b nmax2160 5min B=16 (20 GB P table)", 2160, 16, None, "weights", **kw)
     add("cfg4c nmax2160 5min B=16 (fused recursion kernels, no P table)", 2160, 16, None, "weights", flags=capi.FLAG_NO_PTABLE, **kw)
     add("cfg4d nmax2160 5min B=64 (20 GB P table)", 2160, 64, None, "weights", **kw)
-    json.dump(out, open("gpurun_out/configs_r01.json", "w"), indent=1)
+    json.dump(out, open("gpurun_out/configs_r02.json", "w"), indent=1)
