@@ -234,6 +234,9 @@ struct TA {
     // hand its registers to the consumers (setmaxnreg works on whole warpgroups)
     static constexpr int NCONS = 256, NTHREADS = 384;
     static constexpr int REGS_CONSUMER = 232, REGS_PRODUCER = 40;
+    // the register pool is what the CTA was launched with: 384 threads x 168 registers = 8 warps x 232 + 4 warps x 40 exactly.  A
+    // producer share of 48 leaves the consumers' setmaxnreg.inc waiting for registers that never come (r02: the kernel hung)
+    static_assert(8 * REGS_CONSUMER + 4 * REGS_PRODUCER <= 12 * 168, "setmaxnreg: more registers requested than the CTA owns");
     static constexpr int GSZ = RT * 2 * CROW;         // [32 rows][E/O][grow] doubles
     static constexpr int PSZ = 2 * NDG * PT_SUB;      // 2 NDG 16-degree sub-tiles [16][34]
     static constexpr size_t SMEM = sizeof(double) * (2 * GSZ + PSTAGES * PSZ) + sizeof(uint64_t) * (2 * PSTAGES + 4);
