@@ -13,10 +13,14 @@ __device__ __forceinline__ double2 mul_mi(double2 a, double s) { return make_dou
 
 // ------------------------------------------------------------------------------------------------
 // Dense trig sums.  points != 0: row r has the single longitude lonr[i1[r]] (point mode).
-// thread <-> (row, longitude index); loops orders; fields innermost.
+// thread <-> (row, longitude index); one group of GS fields (their cosine and sine columns are adjacent in G: 2*GS contiguous
+// doubles per parity) at a time with the sums of the group in registers, orders innermost: sincos(m*lonr) is evaluated once
+// per (point, order, group) instead of once per field (r01), in the reference's order of operations (Ynm.hpp:114,127), and
+// the order sum of every field runs m = 0, 1, ... exactly as before (bit-identical results).
+template <int GS>
 __global__ void __launch_bounds__(128) k_lon_syn_dense(DevTables t, int batch, int points, const double* __restrict__ G,
                                                        double* __restrict__ grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon) {
-    const int N = t.nmax, R = t.nrows, NC = t.NC, Bp = t.Bp;
+    const int N = t.nmax, R = t.nrows;
     const int nl = points ? 1 : t.nlon;
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (int64_t)R * nl) return;
@@ -24,48 +28,70 @@ __global__ void __launch_bounds__(128) k_lon_syn_dense(DevTables t, int batch, i
     const int j = (int)(gid - (int64_t)row * nl);
     const int i1 = t.row_i1[row], i2 = t.row_i2[row];
     const double lonr = points ? t.lonr[i1] : t.lonr[j];
-    for (int b = 0; b < batch; ++b) {
-        double s1 = 0.0, s2 = 0.0;
-        for (int m = 0; m <= N; ++m) {
+    const int64_t gstep = (int64_t)R * 2 * t.Gs;
+    for (int b0 = 0; b0 < batch; b0 += GS) {
+        double s1[GS], s2[GS];
+#pragma unroll
+        for (int f = 0; f < GS; ++f) { s1[f] = 0.0; s2[f] = 0.0; }
+        const double* g = G + ((int64_t)row * 2) * t.Gs + colidx(0, b0, GS);
+        for (int m = 0; m <= N; ++m, g += gstep) {
             double sn, cs;
             sincos((double)m * lonr, &sn, &cs);   // Ynm.hpp:127
-            const double* g = G + (((int64_t)m * R + row) * 2) * t.Gs;
-            const int cc = colidx(0, b, t.GS), sc = colidx(1, b, t.GS);
-            double Ec = g[cc], Es = g[sc], Oc = g[t.Gs + cc], Os = g[t.Gs + sc];
-            s1 += (Ec + Oc) * cs + (Es + Os) * sn;
-            s2 += (Ec - Oc) * cs + (Es - Os) * sn;
+#pragma unroll
+            for (int f = 0; f < GS; ++f) {
+                const double Ec = g[f], Es = g[GS + f], Oc = g[t.Gs + f], Os = g[t.Gs + GS + f];
+                s1[f] += (Ec + Oc) * cs + (Es + Os) * sn;
+                s2[f] += (Ec - Oc) * cs + (Es - Os) * sn;
+            }
         }
-        int64_t off = (int64_t)b * gs_b + (points ? 0 : (int64_t)j * gs_lon);
-        grid[off + (int64_t)i1 * gs_lat] = s1;
-        if (i2 >= 0) grid[off + (int64_t)i2 * gs_lat] = s2;
+#pragma unroll
+        for (int f = 0; f < GS; ++f) {
+            if (b0 + f >= batch) break;
+            const int64_t off = (int64_t)(b0 + f) * gs_b + (points ? 0 : (int64_t)j * gs_lon);
+            grid[off + (int64_t)i1 * gs_lat] = s1[f];
+            if (i2 >= 0) grid[off + (int64_t)i2 * gs_lat] = s2[f];
+        }
     }
 }
 
-// thread <-> (row, order m); loops longitudes; fields innermost (sequential, deterministic)
+// thread <-> (row, order m); one group of GS fields at a time, longitudes innermost (sequential, deterministic; same sums as r01)
+template <int GS>
 __global__ void __launch_bounds__(128) k_lon_ana_dense(DevTables t, int batch, const double* __restrict__ grid, int64_t gs_b,
                                                        int64_t gs_lat, int64_t gs_lon, double* __restrict__ G) {
-    const int N = t.nmax, R = t.nrows, NC = t.NC, Bp = t.Bp;
+    const int N = t.nmax, R = t.nrows, Bp = t.Bp;
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (int64_t)R * (N + 1)) return;
     const int row = (int)(gid / (N + 1));
     const int m = (int)(gid - (int64_t)row * (N + 1));
     const int i1 = t.row_i1[row], i2 = t.row_i2[row];
     const double w1 = t.w1[row], w2 = t.w2[row];
-    for (int b = 0; b < Bp; ++b) {
-        double a = 0, bb = 0, ap = 0, bp = 0;
-        if (b < batch) {
+    for (int b0 = 0; b0 < Bp; b0 += GS) {
+        double a[GS], bb[GS], ap[GS], bp[GS];
+#pragma unroll
+        for (int f = 0; f < GS; ++f) { a[f] = 0.0; bb[f] = 0.0; ap[f] = 0.0; bp[f] = 0.0; }
+        const int nf = min(GS, batch - b0);            // live fields of the group (<= 0: padded group, zeros)
+        if (nf > 0) {
+            const double* r1 = grid + (int64_t)b0 * gs_b + (int64_t)i1 * gs_lat;
+            const double* r2 = grid + (int64_t)b0 * gs_b + (int64_t)(i2 >= 0 ? i2 : i1) * gs_lat;
             for (int j = 0; j < t.nlon; ++j) {
                 double sn, cs;
                 sincos((double)m * t.lonr[j], &sn, &cs);
-                double f1 = grid[(int64_t)b * gs_b + (int64_t)i1 * gs_lat + (int64_t)j * gs_lon];
-                double f2 = i2 >= 0 ? grid[(int64_t)b * gs_b + (int64_t)i2 * gs_lat + (int64_t)j * gs_lon] : 0.0;
-                a += f1 * cs; bb += f1 * sn; ap += f2 * cs; bp += f2 * sn;
+#pragma unroll
+                for (int f = 0; f < GS; ++f) {
+                    if (f < nf) {
+                        const double f1 = r1[(int64_t)f * gs_b + (int64_t)j * gs_lon];
+                        const double f2 = i2 >= 0 ? r2[(int64_t)f * gs_b + (int64_t)j * gs_lon] : 0.0;
+                        a[f] += f1 * cs; bb[f] += f1 * sn; ap[f] += f2 * cs; bp[f] += f2 * sn;
+                    }
+                }
             }
-            a *= w1; bb *= w1; ap *= w2; bp *= w2;
         }
-        double* g = G + (((int64_t)m * R + row) * 2) * t.Gs;
-        const int cc = colidx(0, b, t.GS), sc = colidx(1, b, t.GS);
-        g[cc] = a + ap; g[sc] = bb + bp; g[t.Gs + cc] = a - ap; g[t.Gs + sc] = bb - bp;
+        double* g = G + (((int64_t)m * R + row) * 2) * t.Gs + colidx(0, b0, GS);
+#pragma unroll
+        for (int f = 0; f < GS; ++f) {
+            const double A = a[f] * w1, B = bb[f] * w1, Ap = ap[f] * w2, Bq = bp[f] * w2;
+            g[f] = A + Ap; g[GS + f] = B + Bq; g[t.Gs + f] = A - Ap; g[t.Gs + GS + f] = B - Bq;
+        }
     }
 }
 
@@ -80,7 +106,8 @@ int launch_lon_syn(const Plan& p, int batch, double* grid, int64_t gs_b, int64_t
     int64_t tot = (int64_t)p.nrows * nl;
     dim3 g((unsigned)((tot + 127) / 128));
     trace_kernel(p, "k_lon_syn_dense");
-    k_lon_syn_dense<<<g, 128, 0, st>>>(p.t, batch, points, p.G, grid, gs_b, gs_lat, gs_lon);
+    if (p.t.GS == 8) k_lon_syn_dense<8><<<g, 128, 0, st>>>(p.t, batch, points, p.G, grid, gs_b, gs_lat, gs_lon);
+    else k_lon_syn_dense<4><<<g, 128, 0, st>>>(p.t, batch, points, p.G, grid, gs_b, gs_lat, gs_lon);
     return 0;
 }
 
@@ -89,7 +116,8 @@ int launch_lon_ana(const Plan& p, int batch, const double* grid, int64_t gs_b, i
     int64_t tot = (int64_t)p.nrows * (p.nmax + 1);
     dim3 g((unsigned)((tot + 127) / 128));
     trace_kernel(p, "k_lon_ana_dense");
-    k_lon_ana_dense<<<g, 128, 0, st>>>(p.t, batch, grid, gs_b, gs_lat, gs_lon, p.G);
+    if (p.t.GS == 8) k_lon_ana_dense<8><<<g, 128, 0, st>>>(p.t, batch, grid, gs_b, gs_lat, gs_lon, p.G);
+    else k_lon_ana_dense<4><<<g, 128, 0, st>>>(p.t, batch, grid, gs_b, gs_lat, gs_lon, p.G);
     return 0;
 }
 
