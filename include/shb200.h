@@ -239,6 +239,12 @@ int shb200_debug_legendre(int32_t device, int32_t nmax, double lat_deg, double* 
  * outermost axis, dense stride of each axis. */
 int shb200_debug_host_copy(int32_t nax, const int64_t* ext, const int64_t* strides, double* host, double* dense, int32_t to_dense, int64_t* info);
 
+/* Debug/measurement hook: cycle counters of the three-pass longitude kernels (lon_fft3.cu).  enable != 0 switches the
+ * counting on (thread 0 of every CTA adds its clock64 deltas), 0 off; the current sums are copied to out (16 values, may be
+ * NULL: synthesis [CTAs, assembly, pass 0, pass 1, last pass + row stores], then analysis [CTAs, table fill, first pass + row
+ * loads, pass 1, pass 0, spectrum pick-up]) and cleared. */
+int shb200_debug_fft_cycles(int32_t enable, int64_t* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,7 +24,7 @@ EXPORTS = [
     "shb200_gauss_nodes", "shb200_debug_legendre", "shb200_plan_stage_times", "shb200_plan_last_kernels", "shb200_roundtrip_host",
     "shb200_host_alloc", "shb200_host_free", "shb200_host_trim", "shb200_debug_host_copy",
     "shb200_shard_size", "shb200_analysis_packed", "shb200_unpack_shards", "shb200_scatter_rows", "shb200_apply_mask",
-    "shb200_gfc_parse", "shb200_parse_floats", "shb200_scatter_nm", "shb200_polygon_mask",
+    "shb200_gfc_parse", "shb200_parse_floats", "shb200_scatter_nm", "shb200_polygon_mask", "shb200_debug_fft_cycles",
 ]
 VERSION = 200
 
@@ -95,6 +95,7 @@ def lib():
     L.shb200_host_alloc.argtypes = [i64, C.POINTER(vp)]
     L.shb200_host_free.argtypes = [vp]
     L.shb200_host_trim.argtypes = []
+    L.shb200_debug_fft_cycles.argtypes = [i32, vp]
     L.shb200_debug_host_copy.argtypes = [i32, vp, vp, vp, vp, i32, vp]
     L.shb200_shard_size.argtypes = [i32, i32, i32]
     L.shb200_analysis_packed.argtypes = [vp, i32, vp, i64, i64, i64, vp, i64, vp, po]

@@ -40,6 +40,7 @@ struct DevTables {
     // longitude stage
     const double2* tw;    // [K] exp(-2 pi i k / K)
     const double2* phase; // [nmax+1] exp(+i m lon0)
+    int phase_unit;       // 1: lon0 == 0, every phase factor is exactly 1
     const double* lonr;   // [nlon] lon*pi/180 (dense path; Ynm.hpp:114)
     // nm packing
     const int64_t* slot_src;  // [tri_size*2] index into the user nm list for (slot, cos/sin) or -1
@@ -91,6 +92,9 @@ int launch_lon_syn(const Plan& p, int batch, double* grid, int64_t gs_b, int64_t
 int launch_lon_ana(const Plan& p, int batch, const double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, cudaStream_t st);
 bool lon_fft_supported(int K, int Bp);
 void lon_fft_perm(int K, int Bp, std::vector<int>& perm);
+// three-pass composite-radix kernels (lon_fft3.cu)
+bool lon_fft3_plan(int K, int Bp, int* group_size);
+void lon_fft3_perm(int K, std::vector<int>& perm);
 
 struct Plan {
     int device = 0, nmax = 0, maxB = 0, Bp = 0, NC = 0;
@@ -102,6 +106,7 @@ struct Plan {
     bool dmma = false;
     int K = 0;
     const int* fft_perm = nullptr;   // device [K] digit-reversal table of the in-place FFT
+    const int* fft3_perm = nullptr;  // device [K] digit-reversal table of the three-pass kernels (null: length not covered)
     int64_t workspace_bytes = 0;
     DevTables t{};
     // owned device memory

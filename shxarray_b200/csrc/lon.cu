@@ -98,9 +98,14 @@ __global__ void __launch_bounds__(128) k_lon_ana_dense(DevTables t, int batch, c
 // ------------------------------------------------------------------------------------------------
 int launch_lon_syn_fft(const Plan& p, int batch, double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, cudaStream_t st);
 int launch_lon_ana_fft(const Plan& p, int batch, const double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, cudaStream_t st);
+int launch_lon_syn_fft3(const Plan& p, int batch, double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, cudaStream_t st);
+int launch_lon_ana_fft3(const Plan& p, int batch, const double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, cudaStream_t st);
 
 int launch_lon_syn(const Plan& p, int batch, double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, cudaStream_t st) {
-    if (p.lon_fft) return launch_lon_syn_fft(p, batch, grid, gs_b, gs_lat, gs_lon, st);
+    if (p.lon_fft) {
+        const int rc3 = launch_lon_syn_fft3(p, batch, grid, gs_b, gs_lat, gs_lon, st);
+        return rc3 >= 0 ? rc3 : launch_lon_syn_fft(p, batch, grid, gs_b, gs_lat, gs_lon, st);
+    }
     int points = p.mode == SHB200_MODE_POINTS;
     int nl = points ? 1 : p.nlon;
     int64_t tot = (int64_t)p.nrows * nl;
@@ -112,7 +117,10 @@ int launch_lon_syn(const Plan& p, int batch, double* grid, int64_t gs_b, int64_t
 }
 
 int launch_lon_ana(const Plan& p, int batch, const double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, cudaStream_t st) {
-    if (p.lon_fft) return launch_lon_ana_fft(p, batch, grid, gs_b, gs_lat, gs_lon, st);
+    if (p.lon_fft) {
+        const int rc3 = launch_lon_ana_fft3(p, batch, grid, gs_b, gs_lat, gs_lon, st);
+        return rc3 >= 0 ? rc3 : launch_lon_ana_fft(p, batch, grid, gs_b, gs_lat, gs_lon, st);
+    }
     int64_t tot = (int64_t)p.nrows * (p.nmax + 1);
     dim3 g((unsigned)((tot + 127) / 128));
     trace_kernel(p, "k_lon_ana_dense");

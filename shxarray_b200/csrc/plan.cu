@@ -312,6 +312,12 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
         lon_fft_perm(p.K, p.Bp, perm);
         if ((rc = upload(p, perm, &p.fft_perm))) return rc;
     }
+    int fft3_group = 0;
+    if (p.lon_fft && lon_fft3_plan(p.K, p.Bp, &fft3_group)) {
+        std::vector<int> perm;
+        lon_fft3_perm(p.K, perm);
+        if ((rc = upload(p, perm, &p.fft3_perm))) return rc;
+    }
     if ((rc = upload(p, slot_src, &t.slot_src))) return rc;
     p.ndup = (int64_t)dup_slot.size();
     if ((rc = upload(p, dup_slot, &p.dup_slot))) return rc;
@@ -323,8 +329,8 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
         if ((rc = dev_alloc(p, sizeof(double) * (N + 1), &q))) return rc;
         p.dscale[w] = (double*)q;
     }
-    t.nmax = N; t.nrows = R; t.nlat = d.nlat; t.nlon = d.nlon; t.Bp = p.Bp; t.NC = p.NC; t.GS = p.Bp >= 8 ? 8 : 4;
-    t.Cs = p.NC + 2; t.Gs = p.NC; t.pt_base = nullptr; t.RT32 = 0; t.m0 = 0; t.mstride = 1; t.first_blk = nullptr;
+    t.nmax = N; t.nrows = R; t.nlat = d.nlat; t.nlon = d.nlon; t.Bp = p.Bp; t.NC = p.NC; t.GS = fft3_group ? fft3_group : (p.Bp >= 8 ? 8 : 4);
+    t.Cs = p.NC + 2; t.Gs = p.NC; t.phase_unit = (p.lon_fft && lon0 == 0.0) ? 1 : 0; t.pt_base = nullptr; t.RT32 = 0; t.m0 = 0; t.mstride = 1; t.first_blk = nullptr;
 
     void* ptr;
     // 16 / 64 slack rows: the tensor-core kernels fetch whole 16-degree / 32-row blocks, also past the last order

@@ -284,17 +284,18 @@ def test_plan_used_below_its_max_batch(flags):
 @pytest.mark.parametrize("nmax,B", [(96, 12), (200, 40)])
 def test_shlib_grid_layout_matches_batch_first(engine, nmax, B):
     """[nlat, nlon, B] grids (shlib's own layout, synthesis.pyx:68-71: batch fastest) take the cooperative 64-byte
-    load / store path of the FFT kernels; same arithmetic as the batch-first path, so bit-identical results."""
+    load / store path of the in-place FFT kernels (lon_fft.cu), batch-first grids the three-pass kernels (lon_fft3.cu) where
+    the length has one: same transform, different factorisation, so equal to rounding (1e-13 of the field maximum)."""
     import torch
     g = sb.lonlat_grid(nmax, gtype="gauss")
     c = torch.from_numpy(S.random_coefficients(nmax, B, kaula=False, seed=77)).cuda()
     f_bf = engine.synthesis(c, lon=g["lon"], lat=g["lat"], nmax=nmax)
     f_sh = engine.synthesis(c, lon=g["lon"], lat=g["lat"], nmax=nmax, layout="shlib")
     assert tuple(f_sh.shape) == (len(g["lat"]), len(g["lon"]), B)
-    assert torch.equal(f_sh.permute(2, 0, 1), f_bf)
+    assert float((f_sh.permute(2, 0, 1) - f_bf).abs().max()) <= 1e-13 * float(f_bf.abs().max())
     a_bf = engine.analysis(f_bf, nmax, g["lon"], g["lat"], quadrature="gauss")
     a_sh = engine.analysis(f_sh, nmax, g["lon"], g["lat"], quadrature="gauss", layout="shlib")
-    assert torch.equal(a_sh, a_bf)
+    assert float((a_sh - a_bf).abs().max()) <= 1e-13 * float(a_bf.abs().max())
     assert per_field_err(a_sh.cpu().numpy(), c.cpu().numpy()) <= TOL
 
 
@@ -541,7 +542,8 @@ def test_batch_chunking_and_strided_device_views(engine):
     assert np.array_equal(out_s.cpu().numpy(), ref)
     gt = torch.from_numpy(ref).cuda().permute(1, 2, 0).contiguous().permute(2, 0, 1)   # [B, lat, lon] view of [lat, lon, B] storage
     a_view = engine.analysis(gt, nmax, g["lon"], g["lat"])
-    assert np.array_equal(a_view.cpu().numpy(), engine.analysis(torch.from_numpy(ref).cuda(), nmax, g["lon"], g["lat"]).cpu().numpy())
+    # (the batch-fastest storage takes the in-place FFT kernels, the contiguous one the three-pass kernels: equal to rounding)
+    assert per_field_err(a_view.cpu().numpy(), engine.analysis(torch.from_numpy(ref).cuda(), nmax, g["lon"], g["lat"]).cpu().numpy()) <= 1e-13
     # host arrays of >= 16 fields go through the chunked pipeline (7-field tail chunk: tiny-batch kernels): equal to rounding
     assert per_field_err(a_view.cpu().numpy(), engine.analysis(ref, nmax, g["lon"], g["lat"])) <= 1e-13
 
@@ -607,6 +609,14 @@ def _r2_grid(tag, z):
     return g["lon"], g["lat"]
 
 
+def _same_kernels(got, want):
+    """Exact kernel names, except that the longitude stage of a length with a three-pass kernel (lon_fft3.cu) reports
+    k_lon_*_fft3 where the generic in-place kernel would report k_lon_*_fft<static...> (SHB200_FFT3=0 selects the latter)."""
+    if os.environ.get("SHB200_FFT3", "1") != "0":
+        want = [w.split("<")[0] + "3" if w.startswith("k_lon_") and "fft<static" in w else w for w in want]
+    return got == want
+
+
 R2_SYN = [("cfg3", "r2_syn_cfg3_b64.npz", ["k_pack_n", "k_leg_syn_tab<4>", "k_lon_syn_fft<static/8>"]),
           ("cfg2", "r2_syn_cfg2_b240.npz", ["k_pack_n", "k_leg_syn_tab<4>", "k_lon_syn_fft<static/8>"]),
           ("n2160", "r2_syn_n2160_b16.npz", ["k_pack_n", "k_leg_syn_tab<1>", "k_lon_syn_fft<static>"])]
@@ -626,7 +636,7 @@ def test_r2_synthesis_headline_kernels_vs_oracle(tag, fname, kernels):
     out = torch.empty((B, len(lat), len(lon)), dtype=torch.float64, device="cuda")
     plan.synthesis_dev(B, ct.data_ptr(), ct.stride(0), 1, out.data_ptr(), out.stride(0), out.stride(1), 1, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
-    assert plan.last_kernels() == kernels
+    assert _same_kernels(plan.last_kernels(), kernels), plan.last_kernels()
     rows = torch.as_tensor(z["rows"], device="cuda")
     cols = torch.as_tensor(z["cols"], device="cuda")
     sub = out[:, rows][:, :, cols].cpu().numpy()                     # [B, rows, cols]
@@ -672,7 +682,7 @@ def test_r2_analysis_headline_kernels_vs_oracle(tag, fname, kernels):
     out = torch.empty((B, nsh), dtype=torch.float64, device="cuda")
     plan.analysis_dev(B, grid.data_ptr(), grid.stride(0), grid.stride(1), 1, out.data_ptr(), nsh, 1, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
-    assert plan.last_kernels() == kernels
+    assert _same_kernels(plan.last_kernels(), kernels), plan.last_kernels()
     if B >= 8:
         assert plan.info.dmma == 2
     got = out[:, torch.as_tensor(z["positions"], device="cuda")].cpu().numpy()
@@ -699,7 +709,7 @@ def test_r2_analysis_headline_kernels_vs_oracle(tag, fname, kernels):
         grid[:, ri, torch.as_tensor(cols2, device="cuda")[None, :]] = torch.from_numpy(vals2).cuda()
         plan.analysis_dev(B, grid.data_ptr(), grid.stride(0), grid.stride(1), 1, out.data_ptr(), nsh, 1, torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
-        assert plan.last_kernels() == kernels
+        assert _same_kernels(plan.last_kernels(), kernels), plan.last_kernels()
         O.set_exact_trig(True)
         try:
             ex = O.analysis(vals2, nmax, lon[cols2], lat[rows], kind="port", weight=float(z["weight"]), nthreads=O.max_threads())
