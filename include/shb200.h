@@ -66,7 +66,7 @@ typedef struct shb200_plan_desc {
     double weight;        /* quadrature prefactor, e.g. |dlon*dlat|/(4 pi) in radians (analysis.pyx:57-60) */
     const double* lat_weights; /* host, nlat entries, SHB200_QUAD_LATWEIGHTS only */
     int32_t flags;        /* SHB200_FLAG_* */
-    int32_t ptable_budget_mib; /* largest P_nm table the plan may keep in HBM, MiB; 0 = default: a quarter of the device memory, at most what is free less 4 GiB */
+    int32_t ptable_budget_mib; /* largest P_nm table the plan may keep in HBM, MiB; 0 = default: half of the device memory, at most what is free less 8 GiB */
 } shb200_plan_desc;
 
 typedef struct shb200_plan_info {

@@ -350,13 +350,14 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
         for (int m = 0; m <= N; ++m) ptb[m + 1] = ptb[m] + (N - m + 16) / 16;
         // + 8 sub-tiles of slack: the tall tile shapes of the narrow-column kernels fetch up to 8 sub-tiles at once, also at the very end
         const size_t pt_elems = (size_t)ptb[N + 1] * (p.Rpad / 32) * (16 * 34) + 8 * (16 * 34);
-        // default budget: a quarter of the device's memory (45 GiB on a 180 GB B200), and never more than what is free now
-        // less 4 GiB of headroom.  At nmax 2160 x 1080 row pairs the table is 20 GB; streaming it (2.9 ms at HBM speed) beats
-        // recomputing P_nm per call (the fused kernels) by 6-10 x for multi-field batches.
+        // default budget: half of the device's memory (90 GiB on a 180 GB B200), and never more than what is free now less
+        // 8 GiB of headroom for the caller's grids.  nmax 2160 on shlib's own grid (shlib.pyx:87-92: 5760 x 11520, 2880 mirror
+        // pairs) needs 57 GB -- the table holds the northern rows only -- and 20 GB on the 5' grid; streaming it beats
+        // recomputing P_nm per call (the fused kernels) by 5-8 x for multi-field batches.
         size_t free_b = 0, total_b = 0;
         SHB_CUDA(cudaMemGetInfo(&free_b, &total_b));
         const double mib = 1024.0 * 1024.0;
-        const double auto_mib = std::min((double)total_b / mib / 4.0, (double)free_b / mib - 4096.0);
+        const double auto_mib = std::min((double)total_b / mib / 2.0, (double)free_b / mib - 8192.0);
         const double budget_mib = d.ptable_budget_mib > 0 ? (double)d.ptable_budget_mib : auto_mib;
         const double need_mib = (double)pt_elems * 8.0 / (1024.0 * 1024.0);
         if (need_mib <= budget_mib) {

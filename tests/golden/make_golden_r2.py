@@ -191,6 +191,28 @@ def ana_n2160_b16():
     _analysis_case("r2_ana_n2160_b16.npz", 2160, 16, lon, lat, rows, cols, 7601, weight, per_m=1)
 
 
+def syn_shlib2160_b16():
+    """nmax 2160 on shlib's OWN default grid (shlib.pyx:87-92: 1/32 degree, 5760 x 11520, lon from -180 + 1/64): the grid
+    whose P table (57 GB) exceeded the round-1 budget."""
+    nmax, B, seed = 2160, 16, 7801
+    lon, lat = O.shlib_grid(nmax, "regular")
+    assert len(lat) == 5760 and len(lon) == 11520
+    n, m = O.nm_index(nmax)
+    c = mixed_coefficients(nmax, B, seed)
+    rows = np.array([0, 1, 700, 2879, 2880, 4000, 5000, 5758, 5759])
+    cols = np.linspace(0, 11519, 8).round().astype(int)
+    with timed("synthesis nmax 2160 on the shlib grid B=16"):
+        g = O.synthesis(c, n, m, lon[cols], lat[rows], grid=True, kind=KIND, nthreads=NTHR)
+    save("r2_syn_shlib2160_b16.npz", nmax=nmax, B=B, seed=seed, rows=rows, cols=cols, values=g)
+
+
+def ana_shlib2160_b16():
+    lon, lat = O.shlib_grid(2160, "regular")
+    rows = spread_rows(5760, 12)
+    cols = np.linspace(0, 11519, 8).round().astype(int)
+    _analysis_case("r2_ana_shlib2160_b16.npz", 2160, 16, lon, lat, rows, cols, 7901, O.analysis_weight(lon, lat), per_m=1)
+
+
 def multiply_128():
     """engine.multiply pattern (shtns.py:394-420) entirely through the oracle: two syntheses on the Gauss grid of
     nmax 128+128, pointwise product, analysis with Gauss weights."""

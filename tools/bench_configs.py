@@ -45,7 +45,10 @@ def run(tag, nmax, B, gtype, quad, flags=0, lon=None, lat=None, lw=None, weight=
             stages.update({k: round(v, 4) for k, v in pl.stage_times().items() if v > 0})
         except Exception:
             pass
-    res = dict(config=tag, nmax=nmax, batch=B, grid=[len(lat), len(lon)], synthesis_ms=t_s, analysis_ms=t_a,
+    vis = {}
+    for pl in plans:
+        vis = dict(synthesis=pl.info.legendre_visited_synthesis, analysis=pl.info.legendre_visited_analysis)
+    res = dict(config=tag, nmax=nmax, batch=B, grid=[len(lat), len(lon)], synthesis_ms=t_s, analysis_ms=t_a, legendre_visited=vis,
                fields_per_s_roundtrip=B / ((t_s + t_a) * 1e-3), roundtrip_rel_err=err, kernels=str(info), stages_ms=stages)
     print(json.dumps(res), flush=True)
     eng.clear()
@@ -74,4 +77,6 @@ if __name__ == "__main__":
     add("cfg4b nmax2160 5min B=16 (20 GB P table)", 2160, 16, None, "weights", **kw)
     add("cfg4c nmax2160 5min B=16 (fused recursion kernels, no P table)", 2160, 16, None, "weights", flags=capi.FLAG_NO_PTABLE, **kw)
     add("cfg4d nmax2160 5min B=64 (20 GB P table)", 2160, 64, None, "weights", **kw)
+    # shlib's own default grid at nmax 2160 (shlib.pyx:87-92: 5760 x 11520): 57 GB P table, longitude length 11520
+    add("cfg4e nmax2160 shlib grid 5760x11520 B=16 (57 GB P table)", 2160, 16, "regular", "shlib")
     json.dump(out, open("gpurun_out/configs_r02.json", "w"), indent=1)
