@@ -1,22 +1,23 @@
 #!/usr/bin/env python
 """Rebuild the tracked profile artefacts from one gpurun session (run here, after the GPU call):
-  gpurun_out/bench_r01_final.json, r01_launches.csv, prof_r01_final.ncu-rep  ->  profiles/
-usage: python tools/refresh_profiles.py"""
+  gpurun_out/bench_{TAG}.json, {TAG}_launches.csv, prof_{TAG}.ncu-rep  ->  profiles/
+usage: python tools/refresh_profiles.py [tag]      (tag = r02 ...: the one given to tools/gpu_session.sh)"""
 import csv, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r02"
 
 def sh(cmd):
     return subprocess.run(cmd, shell=True, capture_output=True, text=True).stdout
 
 # 1. bench line
-b = json.loads(open(f"{G}/bench_r01_final.json").read().strip().splitlines()[-1])
-open(f"{P}/bench_r01_final.json", "w").write(json.dumps(b) + "\n")
-if os.path.exists(f"{G}/bench_r01_reference.json"):
-    open(f"{P}/bench_r01_reference.json", "w").write(open(f"{G}/bench_r01_reference.json").read().strip().splitlines()[-1] + "\n")
+b = json.loads(open(f"{G}/bench_{TAG}.json").read().strip().splitlines()[-1])
+open(f"{P}/bench_{TAG}.json", "w").write(json.dumps(b) + "\n")
+if os.path.exists(f"{G}/bench_{TAG}_reference.json"):
+    open(f"{P}/bench_{TAG}_reference.json", "w").write(open(f"{G}/bench_{TAG}_reference.json").read().strip().splitlines()[-1] + "\n")
 # 2. launch list + shares
-src = open(f"{G}/r01_launches.csv").read()
-open(f"{P}/r01_launches.csv", "w").write(src)
+src = open(f"{G}/{TAG}_launches.csv").read()
+open(f"{P}/{TAG}_launches.csv", "w").write(src)
 rows = [r for r in csv.reader(src.splitlines()) if len(r) > 5]
 hdr, seq = None, []
 for r in rows:
@@ -44,8 +45,8 @@ def agg(s):
     return a
 
 st = b["roofline"]["stages_ms"]; ssum = sum(st.values())
-with open(f"{P}/r01_launch_shares.txt", "w") as f:
-    f.write("# ncu launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline` (gpu__time_duration.sum, --clock-control none), final build of round 1\n"
+with open(f"{P}/{TAG}_launch_shares.txt", "w") as f:
+    f.write(f"# ncu launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline` (gpu__time_duration.sum, --clock-control none), build of {TAG}\n"
             "# per-launch times are cold-cache and serialised: compare SHARES with bench.py's stages_ms, not absolutes\n")
     for title, s in (("device-resident steps (warm-up + timed + stage-timing pass: 64-field launches, <4> tile shapes)", seq[:cut]),
                      ("host-path e2e loop (shb200_*_host: four 16-field chunks per call, <1> tile shapes)", seq[cut:])):
@@ -57,9 +58,9 @@ with open(f"{P}/r01_launch_shares.txt", "w") as f:
     for k, v in st.items():
         f.write(f"{k:16s} {v:7.4f} ms  {100*v/ssum:5.1f}%\n")
 # 3. full capture: summary, traffic, stall profiles
-raw = sh(f"ncu -i {G}/prof_r01_final.ncu-rep --page raw --csv 2>/dev/null")
+raw = sh(f"ncu -i {G}/prof_{TAG}.ncu-rep --page raw --csv 2>/dev/null")
 open("/tmp/final_raw.csv", "w").write(raw)
-open(f"{P}/r01_ncu_full_summary.txt", "w").write(sh(f"python {ROOT}/tools/ncu_raw_summary.py /tmp/final_raw.csv"))
+open(f"{P}/{TAG}_ncu_full_summary.txt", "w").write(sh(f"python {ROOT}/tools/ncu_raw_summary.py /tmp/final_raw.csv"))
 rr = list(csv.reader(raw.splitlines()))
 h, units = rr[0], rr[1]; idx = {x: i for i, x in enumerate(h)}
 mul = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -67,11 +68,11 @@ tr = {}
 for r in rr[2:]:
     name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").split("<")[0].replace("fft::", "").replace("shb::", "")
     tr[name] = {k2: float(r[idx[k1]].replace(",", "")) * mul[units[idx[k1]]] for k1, k2 in (("dram__bytes_read.sum", "dram_bytes_read"), ("dram__bytes_write.sum", "dram_bytes_write"))}
-json.dump({"source": "ncu --set full --clock-control none, profiles/r01_ncu_full_summary.txt (one launch each, cfg3, final build of round 1)", "kernels": tr},
-          open(f"{P}/r01_traffic.json", "w"), indent=1)
+json.dump({"source": f"ncu --set full --clock-control none, profiles/{TAG}_ncu_full_summary.txt (one launch each, cfg3, build of {TAG})", "kernels": tr},
+          open(f"{P}/{TAG}_traffic.json", "w"), indent=1)
 for k in ("k_leg_ana_tab", "k_leg_syn_tab", "k_lon_ana_fft", "k_lon_syn_fft"):
-    sh(f"ncu -i {G}/prof_r01_final.ncu-rep --page source --csv --kernel-name regex:{k} > /tmp/src_{k}.csv 2>/dev/null")
+    sh(f"ncu -i {G}/prof_{TAG}.ncu-rep --page source --csv --kernel-name regex:{k} > /tmp/src_{k}.csv 2>/dev/null")
     body = sh(f"python {ROOT}/tools/ncu_src_summary.py /tmp/src_{k}.csv 24 | cut -c1-200")
-    open(f"{P}/r01_stalls_{k}.txt", "w").write(f"# ncu --set full --import-source on, source page of {k} (profiles/r01_ncu_full_summary.txt is the same capture, final build of round 1): top SASS lines by stall samples\n" + body)
-print(open(f"{P}/r01_launch_shares.txt").read())
+    open(f"{P}/{TAG}_stalls_{k}.txt", "w").write(f"# ncu --set full --import-source on, source page of {k} (profiles/{TAG}_ncu_full_summary.txt is the same capture, build of {TAG}): top SASS lines by stall samples\n" + body)
+print(open(f"{P}/{TAG}_launch_shares.txt").read())
 print(list(tr))
