@@ -233,6 +233,11 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
+    # host locality before the library creates its copy threads / page-locked buffers: stay on the GPU's NUMA node (restored
+    # before the CPU baseline runs, which uses every core it is allowed)
+    from shxarray_b200 import affinity
+    cpus_before = os.sched_getaffinity(0)
+    numa = affinity.bind_to_device_numa(local) if not os.environ.get("SHB200_NO_NUMA_BIND") else {"bound": False, "reason": "SHB200_NO_NUMA_BIND"}
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
@@ -433,9 +438,10 @@ def main():
            "ms_per_step": t_plugin * 1e3, "roundtrip_max_rel_err": e2e_err,
            "pinned_c_abi": {"value": v_pinned, "ms_per_step": t_pinned * 1e3, "path": "shb200_synthesis_host + shb200_analysis_host, all buffers page-locked"},
            "fused_roundtrip": {"value": v_fused, "ms_per_step": t_fused * 1e3, "path": "shb200_roundtrip_host (grid to the host and back, pipelined)", "roundtrip_max_rel_err": fused_err},
-           "pcie": pcie, "pcie_floor_ms_per_step": t_floor * 1e3,
+           "pcie": pcie, "pcie_floor_ms_per_step": t_floor * 1e3, "numa_bind": numa,
            "frac_of_pcie_floor": {"plugin": t_floor / t_plugin, "pinned_c_abi": t_floor / t_pinned, "fused_roundtrip": t_floor / t_fused}}
     del grid_h, out_h, c_pin
+    os.sched_setaffinity(0, cpus_before)
 
     launches = args.steps * (plan.info.launches_synthesis + plan.info.launches_analysis)
     cfg4 = None

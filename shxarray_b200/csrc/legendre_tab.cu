@@ -163,7 +163,10 @@ __global__ void __launch_bounds__(TS<NWC>::NTHREADS, 1) k_leg_syn_tab(DevTables 
             const int m = tile / nrt, rt = tile - m * nrt;
             const int nchunks = (N - m + CH) / CH;
             const int row0 = rt * TR;
-            const bool wlive = row0 + 32 * wr < R;      // this warp's 32 rows exist (last row tile of a tall tile shape)
+            // 8-row groups of this warp that hold latitude rows: 4 except in the last row tile (cfg3: 362 row pairs = 5 tiles of
+            // 64 + 42 -> the second warp row of the last tile owns 10 rows).  0: nothing to do; <= 2: the half-width body below
+            // (a predicated-off DMMA still takes its issue slot, r01; a separate straight-line body does not)
+            const int ng = min(4, max(0, (R - row0 - 32 * wr + 7) >> 3));
             double acc[2][4][4][2];
 #pragma unroll
             for (int e = 0; e < 2; ++e)
@@ -180,24 +183,42 @@ __global__ void __launch_bounds__(TS<NWC>::NTHREADS, 1) k_leg_syn_tab(DevTables 
                 // has been consumed by DMMAs issued in the previous loop iteration.
                 if (prev >= 0) { __syncwarp(); if (lane == 0) mbar_arrive(&empty[prev]); }
                 prev = s;
-                if (NWC < 4 && !wlive) continue;
+                if (ng == 0) continue;
                 const double* __restrict__ SP = stg + s * C_::STAGE + wr * PT_SUB + lr;
                 const double* __restrict__ SC = stg + s * C_::STAGE + C_::PSZ + 32 * wc + lr;
+                if (ng > 2) {
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks)
+                    for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int j = 8 * ks + 2 * lk + e;
-                        double A[4], B[4];
+                        for (int e = 0; e < 2; ++e) {
+                            const int j = 8 * ks + 2 * lk + e;
+                            double A[4], B[4];
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) A[g] = SP[j * 34 + 8 * g];
+                            for (int g = 0; g < 4; ++g) A[g] = SP[j * 34 + 8 * g];
 #pragma unroll
-                        for (int cb = 0; cb < 4; ++cb) B[cb] = SC[j * crow + 8 * cb];
+                            for (int cb = 0; cb < 4; ++cb) B[cb] = SC[j * crow + 8 * cb];
 #pragma unroll
-                        for (int g = 0; g < 4; ++g)
+                            for (int g = 0; g < 4; ++g)
 #pragma unroll
-                            for (int cb = 0; cb < 4; ++cb) dmma(acc[e][g][cb][0], acc[e][g][cb][1], A[g], B[cb]);
-                    }
+                                for (int cb = 0; cb < 4; ++cb) dmma(acc[e][g][cb][0], acc[e][g][cb][1], A[g], B[cb]);
+                        }
+                } else {
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int j = 8 * ks + 2 * lk + e;
+                            double A[2], B[4];
+#pragma unroll
+                            for (int g = 0; g < 2; ++g) A[g] = SP[j * 34 + 8 * g];
+#pragma unroll
+                            for (int cb = 0; cb < 4; ++cb) B[cb] = SC[j * crow + 8 * cb];
+#pragma unroll
+                            for (int g = 0; g < 2; ++g)
+#pragma unroll
+                                for (int cb = 0; cb < 4; ++cb) dmma(acc[e][g][cb][0], acc[e][g][cb][1], A[g], B[cb]);
+                        }
+                }
             }
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
