@@ -114,6 +114,7 @@ struct Plan {
     double* Cm = nullptr;   // [tri_size (+16 slack rows)][Cs]
     double* G = nullptr;    // [(nmax+1)][nrows][2][Gs] (+64 slack rows)
     double* Ptab = nullptr; // tiled device-resident P_nm table (legendre_tab.cu) or null
+    int* ana_prog = nullptr;   // tiny-batch plans: progress counters of the row-tile chain of k_leg_ana_small, [orders][column blocks][16]
     int Rpad = 0;
     // polar skipping (table kernels): tile lists of the persistent synthesis kernel, heaviest tile first, for its three tile
     // shapes (32 * {2, 4, 8} rows); fraction of the (n, m, row) triples visited per shape (synthesis) / stage width (analysis)

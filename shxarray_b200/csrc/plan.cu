@@ -341,6 +341,10 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
     p.G = (double*)ptr;
     SHB_CUDA(cudaMemset(p.Cm, 0, sizeof(double) * cm_elems));
     SHB_CUDA(cudaMemset(p.G, 0, sizeof(double) * g_elems));
+    if (p.NC <= 24) {      // plans that may run k_leg_ana_small with its row tiles chained across CTAs (legendre_dfma.cu)
+        if ((rc = dev_alloc(p, sizeof(int) * ((size_t)(N + 1) * ((p.NC + 7) / 8) * 16 + 1), &ptr))) return rc;
+        p.ana_prog = (int*)ptr;
+    }
     SHB_CUDA(cudaEventCreateWithFlags(&p.ev_done, cudaEventDisableTiming));
     // device-resident P_nm table for the tensor-core kernels (legendre_tab.cu) when it fits the budget
     if (p.dmma && !(d.flags & SHB200_FLAG_NO_PTABLE) && p.NC >= 32 && d.mode == SHB200_MODE_GRID) {

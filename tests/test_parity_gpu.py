@@ -8,7 +8,9 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, field_norm_err, load_group
+import sys
+
+from conftest import GOLDEN, ROOT, field_norm_err, load_group
 from oracle import oracle as O
 import shxarray_b200 as sb
 from shxarray_b200 import capi, synthetic as S
@@ -973,3 +975,46 @@ def test_polar_skipping_changes_nothing_above_1e_minus_13(nmax, B, gtype):
     assert per_field_err(res["skip"][1], res["all"][1]) <= 1e-13
     inv = np.argsort(perm)
     assert per_field_err(res["shuffled"][0][:, inv, :], res["all"][0]) <= 1e-13
+
+
+_SPLIT_SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1])
+import shxarray_b200 as sb
+from shxarray_b200 import synthetic as S
+nmax = 300
+d = 180.0 / 600
+lat = np.arange(-90 + d / 2, 90, d); lon = np.arange(0, 360, d)
+w = (d * np.pi / 180) ** 2 / (4 * np.pi); lw = np.cos(lat * (np.pi / 180))
+eng = sb.SHEngine(device=0)
+out = {}
+for B in (1, 3):
+    c = torch.from_numpy(S.random_coefficients(nmax, B, kaula=False, seed=5)).cuda()
+    f = eng.synthesis(c, lon=lon, lat=lat, nmax=nmax)
+    for tag, shard in (("full", None), ("s1of4", (1, 4))):
+        a = eng.analysis(f, nmax, lon, lat, quadrature="weights", lat_weights=lw, weight=w, order_shard=shard)
+        out[f"{tag}_{B}"] = a.cpu().numpy()
+        out[f"k_{tag}_{B}"] = np.array(",".join(list(eng._plans.values())[-1].last_kernels()))
+np.savez(sys.argv[2], **out)
+"""
+
+
+@pytest.mark.gpu
+def test_chained_row_tile_split_is_bit_identical(tmp_path):
+    """k_leg_ana_small with its row tiles chained across CTAs (SHB200_ANA_SPLIT=1: what an order shard of a multi-GPU analysis
+    runs) against the sequential tile loop (=0): the same additions in the same order, so every bit must agree -- unsharded
+    and for an order shard, one and three fields (600 latitudes = 300 mirror pairs = several row tiles)."""
+    import subprocess
+    res = {}
+    for mode in ("0", "1"):
+        path = tmp_path / f"split{mode}.npz"
+        env = dict(os.environ, SHB200_ANA_SPLIT=mode)
+        subprocess.run([sys.executable, "-c", _SPLIT_SCRIPT, ROOT, str(path)], check=True, env=env, timeout=600)
+        res[mode] = np.load(path)
+    for key in res["0"].files:
+        if key.startswith("k_"):
+            assert "k_leg_ana_small" in str(res["0"][key]), (key, str(res["0"][key]))
+            continue
+        a0, a1 = res["0"][key], res["1"][key]
+        assert np.isfinite(a0).all() and np.abs(a0).max() > 0
+        assert np.array_equal(a0, a1), (key, float(np.abs(a0 - a1).max()))
