@@ -94,6 +94,9 @@ bool lon_fft_supported(int K, int Bp);
 void lon_fft_perm(int K, int Bp, std::vector<int>& perm);
 // three-pass composite-radix kernels (lon_fft3.cu)
 bool lon_fft3_plan(int K, int Bp, int* group_size);
+// fused point-mode synthesis (points.cu)
+bool points_fused_wanted(int npoints);
+void launch_syn_points(const Plan& p, int batch, double* out, int64_t gs_b, int64_t gs_pt, cudaStream_t st);
 void lon_fft3_perm(int K, std::vector<int>& perm);
 
 struct Plan {
@@ -104,6 +107,7 @@ struct Plan {
     bool full_triangle = true;
     bool lon_fft = false;
     bool dmma = false;
+    bool points_fused = false;   // point mode served by k_syn_points (points.cu): no G array
     int K = 0;
     const int* fft_perm = nullptr;   // device [K] digit-reversal table of the in-place FFT
     const int* fft3_perm = nullptr;  // device [K] digit-reversal table of the three-pass kernels (null: length not covered)
@@ -114,7 +118,7 @@ struct Plan {
     double* Cm = nullptr;   // [tri_size (+16 slack rows)][Cs]
     double* G = nullptr;    // [(nmax+1)][nrows][2][Gs] (+64 slack rows)
     double* Ptab = nullptr; // tiled device-resident P_nm table (legendre_tab.cu) or null
-    int* ana_prog = nullptr;   // tiny-batch plans: progress counters of the row-tile chain of k_leg_ana_small, [orders][column blocks][16]
+    mutable double* ana_scratch = nullptr; mutable size_t ana_scratch_bytes = 0;   // per-tile partial sums of k_leg_ana_small (split mode), grown on first use
     int Rpad = 0;
     // polar skipping (table kernels): tile lists of the persistent synthesis kernel, heaviest tile first, for its three tile
     // shapes (32 * {2, 4, 8} rows); fraction of the (n, m, row) triples visited per shape (synthesis) / stage width (analysis)

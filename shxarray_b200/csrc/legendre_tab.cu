@@ -20,6 +20,7 @@
 // complete_tx) + 8 consumer warps (64 DMMA.8x8x4 per stage each), full/empty mbarrier ring.
 // Plans whose table would not fit the budget fall back to the fused on-the-fly kernels.
 #include <algorithm>
+#include <cstdlib>
 
 #include "internal.h"
 #include "recursion.cuh"
@@ -265,7 +266,7 @@ struct TA {
 
 template <int NCQ>
 __global__ void __launch_bounds__(TA<NCQ>::NTHREADS, 1) k_leg_ana_tab(DevTables t, const double* __restrict__ Ptab, const double* __restrict__ G,
-                                                                       double* __restrict__ Cm) {
+                                                                       double* __restrict__ Cm, int dbg_no_restream) {
     using C_ = TA<NCQ>;
     constexpr int NDG = C_::NDG, RT = C_::RT, NS = C_::NS, SB = C_::SB, NCOLS = C_::NCOLS, PSTAGES = C_::PSTAGES, NCONS = C_::NCONS;
     extern __shared__ __align__(128) unsigned char smraw[];
@@ -314,7 +315,12 @@ __global__ void __launch_bounds__(TA<NCQ>::NTHREADS, 1) k_leg_ana_tab(DevTables 
                 const int gb = it & 1;
                 mbar_wait(&gempty[gb], ((it >> 1) & 1) ^ 1);
                 ++it;
-                {
+                if (dbg_no_restream && sb > 0) {
+                    // measurement only (SHB200_DEBUG_ANA_NO_RESTREAM=1, wrong results): the G tiles of every super-block after the
+                    // first are NOT fetched again -- the time this saves bounds what sharing one G pass between the CTAs of a cluster
+                    // (multicast / DSMEM) could gain
+                    if (lane == 0) mbar_arrive(&gfull[gb]);
+                } else {
                     const int nr = min(RT, R - rt * RT);
                     if (lane == 0) mbar_arrive_expect_tx(&gfull[gb], (uint32_t)(nr * 2 * ncols * 8));
                     __syncwarp();
@@ -447,7 +453,8 @@ static bool launch_ana_tab_ncq(const Plan& p, cudaStream_t st) {
     }
     dim3 grid(ana_order_count(p), (p.NC + C_::NCOLS - 1) / C_::NCOLS);
     trace_kernel(p, NCQ == 4 ? "k_leg_ana_tab<4>" : (NCQ == 2 ? "k_leg_ana_tab<2>" : "k_leg_ana_tab<1>"));
-    k_leg_ana_tab<NCQ><<<grid, C_::NTHREADS, C_::SMEM, st>>>(p.t, p.Ptab, p.G, p.Cm);
+    static const int dbg = [] { const char* e = getenv("SHB200_DEBUG_ANA_NO_RESTREAM"); return e ? atoi(e) : 0; }();
+    k_leg_ana_tab<NCQ><<<grid, C_::NTHREADS, C_::SMEM, st>>>(p.t, p.Ptab, p.G, p.Cm, dbg);
     return true;
 }
 

@@ -334,17 +334,14 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
 
     void* ptr;
     // 16 / 64 slack rows: the tensor-core kernels fetch whole 16-degree / 32-row blocks, also past the last order
-    const size_t cm_elems = ((size_t)T + 16) * t.Cs, g_elems = ((size_t)(N + 1) * R * 2 + 64) * t.Gs;
+    p.points_fused = d.mode == SHB200_MODE_POINTS && points_fused_wanted(R);
+    const size_t cm_elems = ((size_t)T + 16) * t.Cs, g_elems = p.points_fused ? (size_t)64 * t.Gs : ((size_t)(N + 1) * R * 2 + 64) * t.Gs;
     if ((rc = dev_alloc(p, sizeof(double) * cm_elems, &ptr))) return rc;
     p.Cm = (double*)ptr;
     if ((rc = dev_alloc(p, sizeof(double) * g_elems, &ptr))) return rc;
     p.G = (double*)ptr;
     SHB_CUDA(cudaMemset(p.Cm, 0, sizeof(double) * cm_elems));
     SHB_CUDA(cudaMemset(p.G, 0, sizeof(double) * g_elems));
-    if (p.NC <= 24) {      // plans that may run k_leg_ana_small with its row tiles chained across CTAs (legendre_dfma.cu)
-        if ((rc = dev_alloc(p, sizeof(int) * ((size_t)(N + 1) * ((p.NC + 7) / 8) * 16 + 1), &ptr))) return rc;
-        p.ana_prog = (int*)ptr;
-    }
     SHB_CUDA(cudaEventCreateWithFlags(&p.ev_done, cudaEventDisableTiming));
     // device-resident P_nm table for the tensor-core kernels (legendre_tab.cu) when it fits the budget
     if (p.dmma && !(d.flags & SHB200_FLAG_NO_PTABLE) && p.NC >= 32 && d.mode == SHB200_MODE_GRID) {
@@ -403,6 +400,7 @@ static void free_plan(Plan& p) {
     free_host_io(p);
     for (void* d : p.owned) cudaFree(d);
     p.owned.clear();
+    if (p.ana_scratch) { cudaFree(p.ana_scratch); p.ana_scratch = nullptr; p.ana_scratch_bytes = 0; }
     if (p.mul_grid) cudaFree(p.mul_grid);
     if (p.ev_done) cudaEventDestroy(p.ev_done);
     for (int i = 0; i < 8; ++i) if (p.ev[i]) cudaEventDestroy(p.ev[i]);
@@ -472,10 +470,15 @@ int do_synthesis(Plan& p, int batch, const double* coef, int64_t cs_b, int64_t c
     if (tm) cudaEventRecord(p.ev[0], st);
     launch_pack(p, batch, coef, cs_b, cs_nm, st);
     if (tm) cudaEventRecord(p.ev[1], st);
-    launch_legendre_syn(p, st);
-    if (tm) cudaEventRecord(p.ev[2], st);
-    rc = launch_lon_syn(p, batch, grid, gs_b, gs_lat, gs_lon, st);
-    if (rc) return rc;
+    if (p.points_fused) {
+        launch_syn_points(p, batch, grid, gs_b, gs_lat, st);     // Legendre and longitude stage of a point set in one kernel
+        if (tm) cudaEventRecord(p.ev[2], st);
+    } else {
+        launch_legendre_syn(p, st);
+        if (tm) cudaEventRecord(p.ev[2], st);
+        rc = launch_lon_syn(p, batch, grid, gs_b, gs_lat, gs_lon, st);
+        if (rc) return rc;
+    }
     if (tm) { cudaEventRecord(p.ev[3], st); p.timed_syn = true; }
     SHB_CUDA(cudaGetLastError());
     return 0;

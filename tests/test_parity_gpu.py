@@ -1018,3 +1018,32 @@ def test_chained_row_tile_split_is_bit_identical(tmp_path):
         a0, a1 = res["0"][key], res["1"][key]
         assert np.isfinite(a0).all() and np.abs(a0).max() > 0
         assert np.array_equal(a0, a1), (key, float(np.abs(a0 - a1).max()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B", [1, 3, 20])
+def test_point_synthesis_fused_kernel_vs_oracle(B, monkeypatch):
+    """Point sets large enough to fill the GPU run ONE kernel (points.cu: recursion, contraction and trig factor per point, no
+    G array).  Forced here on a small set (SHB200_POINTS_FUSED=1) and compared with the shlib arithmetic (synthesis.pyx:186-189)
+    and with the generic path; poles, the equator and longitudes at 0 / +-180 / 360 included."""
+    nmax, npts = 90, 700
+    rng = np.random.default_rng(17)
+    lon, lat = rng.uniform(-180, 360, npts), rng.uniform(-90, 90, npts)
+    lat[:4] = (90.0, -90.0, 0.0, 89.999999)
+    lon[:6] = (0.0, 180.0, -180.0, 360.0, 12.5, 359.75)
+    c = S.random_coefficients(nmax, B, kaula=False, seed=23)
+    n, m = sb.nm_index(nmax)
+    ref = O.synthesis(c, n, m, lon, lat, grid=False, kind="port").T                      # [B, npoints]
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("SHB200_POINTS_FUSED", mode)
+        eng = sb.SHEngine(device=0)
+        out[mode] = eng.synthesis(c, n, m, lon, lat, points=True)
+        plan = list(eng._plans.values())[-1]
+        assert ("k_syn_points" in plan.last_kernels()) == (mode == "1"), plan.last_kernels()
+        if mode == "1":
+            assert plan.info.workspace_bytes < 64 << 20                                  # no G[m][point] array
+        eng.clear()
+    fmax = np.abs(ref).max(axis=1, keepdims=True)
+    assert (np.abs(out["1"] - ref) / fmax).max() <= TOL
+    assert (np.abs(out["1"] - out["0"]) / fmax).max() <= 1e-13

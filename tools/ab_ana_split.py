@@ -49,5 +49,5 @@ for tag, shard in cases:
         continue
     a, t = timed(lambda: eng.analysis(f, nmax, lon, lat, order_shard=shard, **kw))
     plan = list(eng._plans.values())[-1]
-    res[tag] = {"ms": t, "sha": hashlib.sha256(a.cpu().numpy().tobytes()).hexdigest()[:16], "stages_ms": {k: round(v, 4) for k, v in plan.stage_times().items() if v > 0 and k.startswith("ana")}}
+    res[tag] = {"ms": t, "sha": hashlib.sha256(a.cpu().numpy().tobytes()).hexdigest()[:16], "stages_ms": {k: round(v, 4) for k, v in plan.stage_times().items() if v > 0 and k.startswith("ana")}, "kernels": plan.last_kernels()}
 print(json.dumps(res))
