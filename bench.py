@@ -161,7 +161,9 @@ def run_reference(args, rank):
 def cfg4_sharded(torch, dist, sb, S, rank, world, local, nmax=2160, reps=5):
     """BASELINE config 4 on the N GPUs of the run: ONE nmax-2160 field on the 5' grid (2160 x 4320), synthesis sharded by
     latitude rows, analysis sharded by orders m (distributed.ShardedSH: one ncclAllGather each), against the same
-    transform on one GPU.  Device time (CUDA events), max over ranks.  Extra keys of the N>1 bench line only."""
+    transform on one GPU.  Device time (CUDA events), max over ranks.  Extra keys of the N>1 bench line only.
+    Synthesis exchanges its rows through peer memory (one kernel of NVLink stores into every rank's grid + a 4-byte all-reduce
+    as barrier) where CUDA IPC works, else one ncclAllGather + a row scatter; analysis: one ncclAllGather of packed shards."""
     from shxarray_b200.distributed import ShardedSH
     d = 180.0 / nmax
     h = np.arange(d / 2, 90, d)
@@ -170,7 +172,7 @@ def cfg4_sharded(torch, dist, sb, S, rank, world, local, nmax=2160, reps=5):
     w = (d * np.pi / 180) ** 2 / (4 * np.pi)
     lw = np.cos(lat * (np.pi / 180))
     eng = sb.SHEngine(device=local)
-    sh = ShardedSH(eng)
+    sh = ShardedSH(eng, peer=not os.environ.get("SHB200_NO_PEER"))     # rows exchanged through peer memory (NVLink stores) when the box allows it
     c = torch.from_numpy(S.random_coefficients(nmax, 1, kaula=True)).cuda()
 
     def timed(fn):
@@ -190,7 +192,8 @@ def cfg4_sharded(torch, dist, sb, S, rank, world, local, nmax=2160, reps=5):
 
     akw = dict(quadrature="weights", lat_weights=lw, weight=w)
     f_sh, t_syn = timed(lambda: sh.synthesis_latsharded(c, lon, lat, nmax=nmax))
-    bytes_syn = sh.last_exchange_bytes
+    bytes_syn, how_syn = sh.last_exchange_bytes, sh.last_exchange
+    f_sh = f_sh.clone()         # the peer-memory path returns one of its two exchange buffers
     a_sh, t_ana = timed(lambda: sh.analysis_msharded(f_sh, nmax, lon, lat, **akw))
     bytes_ana = sh.last_exchange_bytes
     f_1, t_syn1 = timed(lambda: eng.synthesis(c, lon=lon, lat=lat, nmax=nmax))
@@ -202,7 +205,7 @@ def cfg4_sharded(torch, dist, sb, S, rank, world, local, nmax=2160, reps=5):
     return {"workload": f"cfg4: ONE field nmax={nmax}, grid {len(lat)}x{len(lon)} (5'), sharded over {world} GPUs",
             "synthesis_latsharded_ms": t_syn, "analysis_msharded_ms": t_ana, "synthesis_1gpu_ms": t_syn1, "analysis_1gpu_ms": t_ana1,
             "speedup_synthesis": t_syn1 / t_syn, "speedup_analysis": t_ana1 / t_ana,
-            "allgather_bytes_synthesis": int(bytes_syn), "allgather_bytes_analysis": int(bytes_ana),
+            "exchange_bytes_synthesis": int(bytes_syn), "exchange_synthesis": how_syn, "allgather_bytes_analysis": int(bytes_ana),
             "analysis_bit_identical_to_1gpu": bool(ok[0].item() == 1.0), "synthesis_max_rel_diff_vs_1gpu": float(-ok[1].item()),
             "collectives_per_transform": 1}
 

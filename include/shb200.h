@@ -226,6 +226,21 @@ int shb200_unpack_shards(int32_t nmax, int32_t world, int32_t batch, const doubl
 int shb200_scatter_rows(int32_t batch, int32_t world, int32_t rmax, int32_t nlon, const double* src, int64_t rank_stride, int64_t src_b,
                         const int32_t* row_of_slot, double* dst, int64_t dst_b, int64_t dst_lat, void* stream);
 
+/* Peer-memory variant of the latitude-sharded exchange (one process per GPU of one NVLink / NVSwitch box): every rank owns a
+ * [batch][nlat][nlon] grid allocated with shb200_peer_alloc, publishes its 64-byte IPC handle (cudaIpcGetMemHandle) to the
+ * other ranks by any means (torch.distributed.all_gather_object in distributed.py), maps theirs with shb200_peer_open, and
+ * after synthesising its own rows calls shb200_push_rows: ONE kernel stores each of its rows at its final place in EVERY rank's
+ * grid (peer stores over NVLink; dst[w] = base pointer of rank w's grid, a HOST array of `world` device pointers, world <= 16).
+ * No gathered staging buffer, no second pass (shb200_scatter_rows), no NCCL all-gather; the ranks only need a barrier before
+ * they read their grid (distributed.py: a stream-ordered one-element all-reduce).  src row i of field b at
+ * src[b*src_b + i*nlon]; rows_dev[i] (device, int32) = its latitude index. */
+int shb200_peer_alloc(int64_t bytes, void** ptr, void* handle64);
+int shb200_peer_open(const void* handle64, void** ptr);
+int shb200_peer_close(void* ptr);
+int shb200_peer_free(void* ptr);
+int shb200_push_rows(int32_t batch, int32_t world, int32_t nown, int32_t nlon, const double* src, int64_t src_b, const int32_t* rows_dev,
+                     void* const* dst, int64_t dst_b, int64_t dst_lat, void* stream);
+
 /* Gauss-Legendre nodes x (ascending in latitude: x = sin(lat), south to north) and weights (sum = 2). */
 int shb200_gauss_nodes(int32_t n, double* x, double* w);
 

@@ -25,6 +25,7 @@ EXPORTS = [
     "shb200_host_alloc", "shb200_host_free", "shb200_host_trim", "shb200_debug_host_copy",
     "shb200_shard_size", "shb200_analysis_packed", "shb200_unpack_shards", "shb200_scatter_rows", "shb200_apply_mask",
     "shb200_gfc_parse", "shb200_parse_floats", "shb200_scatter_nm", "shb200_polygon_mask", "shb200_debug_fft_cycles",
+    "shb200_peer_alloc", "shb200_peer_open", "shb200_peer_close", "shb200_peer_free", "shb200_push_rows",
 ]
 VERSION = 200
 
@@ -101,6 +102,11 @@ def lib():
     L.shb200_analysis_packed.argtypes = [vp, i32, vp, i64, i64, i64, vp, i64, vp, po]
     L.shb200_unpack_shards.argtypes = [i32, i32, i32, vp, i64, i64, vp, i64, i64, vp]
     L.shb200_scatter_rows.argtypes = [i32, i32, i32, i32, vp, i64, i64, vp, vp, i64, i64, vp]
+    L.shb200_peer_alloc.argtypes = [i64, vp, vp]
+    L.shb200_peer_open.argtypes = [vp, vp]
+    L.shb200_peer_close.argtypes = [vp]
+    L.shb200_peer_free.argtypes = [vp]
+    L.shb200_push_rows.argtypes = [i32, i32, i32, i32, vp, i64, vp, vp, i64, i64, vp]
     L.shb200_gfc_parse.argtypes = [vp, i64, C.c_char_p, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp]
     L.shb200_parse_floats.argtypes = [vp, vp, vp, i64, vp, vp, vp]
     L.shb200_scatter_nm.argtypes = [vp, vp, vp, i64, i64, i64, i32, i32, vp, i64, i64, vp]
@@ -187,6 +193,35 @@ def unpack_shards_dev(nmax, world, batch, all_ptr, rank_stride, ps_b, coef_ptr, 
 
 def scatter_rows_dev(batch, world, rmax, nlon, src_ptr, rank_stride, src_b, row_of_slot_ptr, dst_ptr, dst_b, dst_lat, stream=0):
     check(lib().shb200_scatter_rows(int(batch), int(world), int(rmax), int(nlon), src_ptr, rank_stride, src_b, row_of_slot_ptr, dst_ptr, dst_b, dst_lat, stream))
+
+
+def peer_alloc(nbytes):
+    """Device memory that other processes of this box can map (cudaMalloc + IPC handle).  Returns (pointer, 64-byte handle)."""
+    ptr = C.c_void_p()
+    handle = C.create_string_buffer(64)
+    check(lib().shb200_peer_alloc(int(nbytes), C.byref(ptr), handle))
+    return int(ptr.value), handle.raw
+
+
+def peer_open(handle):
+    ptr = C.c_void_p()
+    buf = C.create_string_buffer(bytes(handle), 64)
+    check(lib().shb200_peer_open(buf, C.byref(ptr)))
+    return int(ptr.value)
+
+
+def peer_close(ptr):
+    check(lib().shb200_peer_close(C.c_void_p(int(ptr))))
+
+
+def peer_free(ptr):
+    check(lib().shb200_peer_free(C.c_void_p(int(ptr))))
+
+
+def push_rows_dev(batch, world, nown, nlon, src_ptr, src_b, rows_ptr, dst_ptrs, dst_b, dst_lat, stream=0):
+    """dst_ptrs: sequence of `world` device pointers (base of every rank's grid)."""
+    arr = (C.c_void_p * int(world))(*[C.c_void_p(int(p)) for p in dst_ptrs])
+    check(lib().shb200_push_rows(int(batch), int(world), int(nown), int(nlon), src_ptr, src_b, rows_ptr, arr, dst_b, dst_lat, stream))
 
 
 def host_trim():

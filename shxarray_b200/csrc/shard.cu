@@ -10,6 +10,8 @@
 //
 //  latitude-sharded synthesis: every rank synthesises its mirror-paired rows into its slot of a [W][B][Rmax][K] buffer;
 //  ncclAllGather; k_scatter_rows moves the rows to their place in the [B][L][K] grid.
+#include <cstring>
+
 #include "internal.h"
 
 namespace shb {
@@ -67,6 +69,23 @@ __global__ void __launch_bounds__(256) k_scatter_rows(const double* __restrict__
     }
 }
 
+// own row i of field b -> its final place in the grid of every rank (peer pointers: stores travel over NVLink).
+// CTA = (own row, field, destination rank); 16-byte stores along longitude.
+struct PushDst { double* p[16]; };
+__global__ void __launch_bounds__(256) k_push_rows(PushDst dst, const double* __restrict__ src, int64_t src_b, int nlon, const int32_t* __restrict__ rows,
+                                                   int64_t dst_b, int64_t dst_lat) {
+    const int i = blockIdx.x, b = blockIdx.y, w = blockIdx.z;
+    const double* a = src + (int64_t)b * src_b + (int64_t)i * nlon;
+    double* d = dst.p[w] + (int64_t)b * dst_b + (int64_t)rows[i] * dst_lat;
+    if ((nlon & 1) == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+        const double2* a2 = reinterpret_cast<const double2*>(a);
+        double2* d2 = reinterpret_cast<double2*>(d);
+        for (int x = threadIdx.x; x < nlon / 2; x += blockDim.x) d2[x] = a2[x];
+    } else {
+        for (int x = threadIdx.x; x < nlon; x += blockDim.x) d[x] = a[x];
+    }
+}
+
 int do_analysis_packed(Plan& p, int batch, const double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, double* packed, int64_t ps_b,
                        cudaStream_t st, const CallOpts& o);
 
@@ -107,6 +126,57 @@ int shb200_scatter_rows(int32_t batch, int32_t world, int32_t rmax, int32_t nlon
     if (batch < 1 || world < 1 || rmax < 1 || nlon < 1 || !src || !row_of_slot || !dst) { set_error("scatter_rows: invalid argument"); return SHB200_EINVAL; }
     dim3 g((unsigned)(world * rmax), (unsigned)batch);
     k_scatter_rows<<<g, 256, 0, (cudaStream_t)stream>>>(src, rank_stride, src_b, rmax, nlon, row_of_slot, dst, dst_b, dst_lat);
+    SHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int shb200_peer_alloc(int64_t bytes, void** ptr, void* handle64) {
+    if (bytes <= 0 || !ptr || !handle64) { set_error("peer_alloc: invalid argument"); return SHB200_EINVAL; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void* d = nullptr;
+    if (cudaMalloc(&d, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); set_error("peer_alloc: out of device memory"); return SHB200_ENOMEM; }
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, d) != cudaSuccess) { cudaGetLastError(); cudaFree(d); set_error("peer_alloc: cudaIpcGetMemHandle failed"); return SHB200_EUNSUPPORTED; }
+    memcpy(handle64, &h, 64);
+    *ptr = d;
+    return 0;
+}
+
+int shb200_peer_open(const void* handle64, void** ptr) {
+    if (!handle64 || !ptr) { set_error("peer_open: null argument"); return SHB200_EINVAL; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* d = nullptr;
+    if (cudaIpcOpenMemHandle(&d, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("peer_open: cudaIpcOpenMemHandle failed (no peer access between the two devices?)");
+        return SHB200_EUNSUPPORTED;
+    }
+    *ptr = d;
+    return 0;
+}
+
+int shb200_peer_close(void* ptr) {
+    if (ptr && cudaIpcCloseMemHandle(ptr) != cudaSuccess) { cudaGetLastError(); set_error("peer_close: cudaIpcCloseMemHandle failed"); return SHB200_ECUDA; }
+    return 0;
+}
+
+int shb200_peer_free(void* ptr) {
+    if (ptr && cudaFree(ptr) != cudaSuccess) { cudaGetLastError(); set_error("peer_free: cudaFree failed"); return SHB200_ECUDA; }
+    return 0;
+}
+
+int shb200_push_rows(int32_t batch, int32_t world, int32_t nown, int32_t nlon, const double* src, int64_t src_b, const int32_t* rows_dev,
+                     void* const* dst, int64_t dst_b, int64_t dst_lat, void* stream) {
+    if (batch < 1 || world < 1 || world > 16 || nown < 0 || nlon < 1 || !src || !rows_dev || !dst) { set_error("push_rows: invalid argument (world <= 16)"); return SHB200_EINVAL; }
+    if (nown == 0) return 0;
+    PushDst d{};
+    for (int w = 0; w < world; ++w) {
+        if (!dst[w]) { set_error("push_rows: null destination"); return SHB200_EINVAL; }
+        d.p[w] = (double*)dst[w];
+    }
+    dim3 g((unsigned)nown, (unsigned)batch, (unsigned)world);
+    k_push_rows<<<g, 256, 0, (cudaStream_t)stream>>>(d, src, src_b, nlon, rows_dev, dst_b, dst_lat);
     SHB_CUDA(cudaGetLastError());
     return 0;
 }

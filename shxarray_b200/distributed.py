@@ -143,14 +143,102 @@ class _Dist:
         return buf
 
 
-class ShardedSH:
-    """Batch-, latitude- and order-sharded transforms on top of an engine with the ``SHEngine`` array interface."""
+class _CudaView:
+    """Device memory owned by the C library, exposed through __cuda_array_interface__ so that torch can wrap it without a copy."""
 
-    def __init__(self, engine, group=None):
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+class _PeerGrids:
+    """The grids of all ranks of one box, each mapped into every process (CUDA IPC): the latitude-sharded synthesis stores its
+    rows straight into every rank's grid over NVLink (shb200_push_rows) instead of all-gathering a staging buffer and scattering
+    it.  Two grids per rank, used alternately: a rank may be one exchange ahead of the slowest one, never two (every exchange
+    ends with a barrier), so the grid a slow rank is still reading is never the one being written."""
+
+    def __init__(self, d, capi, torch, device, shape):
+        self.capi, self.shape, self.d = capi, tuple(shape), d
+        nbytes = int(np.prod(shape)) * 8
+        self.own, self.peers, self.opened = [], [], []
+        ok = 1
+        handles = [None, None]
+        try:
+            for k in range(2):
+                ptr, h = capi.peer_alloc(nbytes)
+                self.own.append(ptr)
+                handles[k] = h
+        except Exception:
+            ok = 0
+        gathered = [None] * d.world
+        d.dist.all_gather_object(gathered, (ok, handles), group=d.group)
+        ok = min(g[0] for g in gathered)
+        if ok:
+            try:
+                for k in range(2):
+                    row = []
+                    for r in range(d.world):
+                        if r == d.rank:
+                            row.append(self.own[k])
+                        else:
+                            q = capi.peer_open(gathered[r][1][k])
+                            self.opened.append(q)
+                            row.append(q)
+                    self.peers.append(row)
+            except Exception:
+                ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        d.dist.all_reduce(flag, op=d.dist.ReduceOp.MIN, group=d.group)
+        self.ok = bool(int(flag.item()))
+        self.turn = 0
+        self.token = torch.zeros(1, dtype=torch.int32, device=device)
+        self.grids = [torch.as_tensor(_CudaView(p, shape), device=device) for p in self.own] if self.ok else []
+        if not self.ok:
+            self.close()
+
+    def close(self):
+        for q in self.opened:
+            try:
+                self.capi.peer_close(q)
+            except Exception:
+                pass
+        for p in self.own:
+            try:
+                self.capi.peer_free(p)
+            except Exception:
+                pass
+        self.opened, self.own, self.grids = [], [], []
+
+
+class ShardedSH:
+    """Batch-, latitude- and order-sharded transforms on top of an engine with the ``SHEngine`` array interface.
+
+    peer=True (CUDA tensors, one box): the latitude-sharded synthesis exchanges its rows through peer memory (NVLink stores into
+    every rank's grid, `_PeerGrids`) instead of ncclAllGather + row scatter.  The grid it returns is then one of two exchange
+    buffers of this object and stays valid until the second next call; ``.clone()`` it to keep it longer."""
+
+    def __init__(self, engine, group=None, peer=False):
         self.engine = engine
         self.d = _Dist(group)
         self._slots = {}
+        self._peer = {} if peer else None
         self.last_exchange_bytes = 0      # bytes this rank contributed to + received from the last collective
+        self.last_exchange = "none"
+
+    def _peer_grids(self, shape, device):
+        """Collective on first use per shape (IPC handle exchange); None if peer memory is unavailable on any rank."""
+        if self._peer is None or self.d.world == 1 or self.d.world > 16:
+            return None
+        key = (tuple(shape), str(device))
+        if key not in self._peer:
+            import torch
+            from . import capi
+            for old in self._peer.values():
+                if old is not None:
+                    old.close()
+            self._peer.clear()
+            pg = _PeerGrids(self.d, capi, torch, device, shape)
+            self._peer[key] = pg if pg.ok else None
+        return self._peer[key]
 
     # ---- batch sharding: no collective -------------------------------------------------------------
     def local_batch(self, batch):
@@ -195,7 +283,23 @@ class ShardedSH:
             return rows, self.engine.synthesis(coef, lon=lon, lat=lat[rows], **kw)
         B = coef.shape[0] if coef.ndim == 2 else 1
         K, L = len(lon), len(lat)
+        pg = self._peer_grids((B, L, K), coef.device) if is_t and hasattr(self.engine, "scatter_rows") else None
+        if pg is not None:
+            from . import capi
+            local = self.engine.synthesis(coef, lon=lon, lat=lat[rows], **kw)             # [B, own rows, K]
+            rows_dev = ros[rank * rmax:rank * rmax + len(rows)]
+            k = pg.turn
+            pg.turn ^= 1
+            stream = torch.cuda.current_stream(coef.device).cuda_stream
+            capi.push_rows_dev(B, W, len(rows), K, local.data_ptr(), local.stride(0), rows_dev.data_ptr(), pg.peers[k], L * K, K, stream)
+            self.engine.launches += 1
+            # barrier: every rank's push kernel has completed (stream order) before any rank reads its grid
+            self.d.dist.all_reduce(pg.token, group=self.d.group)
+            self.last_exchange_bytes = B * len(rows) * K * 8 * W
+            self.last_exchange = "peer stores (shb200_push_rows) + 4-byte all-reduce as barrier"
+            return pg.grids[k]
         if is_t and hasattr(self.engine, "scatter_rows"):
+            self.last_exchange = "ncclAllGather + shb200_scatter_rows"
             buf = torch.empty((W, B, rmax, K), dtype=torch.float64, device=coef.device)
             self.engine.synthesis(coef, lon=lon, lat=lat[rows], out=buf[rank][:, :len(rows), :], **kw)
             self.d.all_gather_inplace(buf)

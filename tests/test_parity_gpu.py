@@ -1047,3 +1047,32 @@ def test_point_synthesis_fused_kernel_vs_oracle(B, monkeypatch):
     fmax = np.abs(ref).max(axis=1, keepdims=True)
     assert (np.abs(out["1"] - ref) / fmax).max() <= TOL
     assert (np.abs(out["1"] - out["0"]) / fmax).max() <= 1e-13
+
+
+@pytest.mark.gpu
+def test_push_rows_and_peer_allocation_single_gpu():
+    """The kernel of the peer-memory row exchange (shb200_push_rows: own rows -> their final place in EVERY rank's grid) with
+    three local tensors standing in for the ranks' grids (odd and even row lengths: 8- and 16-byte store paths), and the
+    IPC-capable allocation wrapped as a torch tensor without a copy (distributed._CudaView).  The cross-process part (handle
+    exchange, NVLink stores) is exercised by bench.py at N > 1 (cfg4_sharded.exchange_synthesis)."""
+    import torch
+    from shxarray_b200.distributed import _CudaView
+    for K in (10, 7):
+        B, L, W = 2, 12, 3
+        rows = torch.tensor([1, 10, 4, 7], dtype=torch.int32, device="cuda")
+        src = torch.randn(B, 4, K, dtype=torch.float64, device="cuda")
+        dsts = [torch.zeros(B, L, K, dtype=torch.float64, device="cuda") for _ in range(W)]
+        capi.push_rows_dev(B, W, 4, K, src.data_ptr(), src.stride(0), rows.data_ptr(), [d.data_ptr() for d in dsts], L * K, K,
+                           torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        want = torch.zeros(B, L, K, dtype=torch.float64, device="cuda")
+        want[:, rows.long()] = src
+        for d in dsts:
+            assert torch.equal(d, want)
+    ptr, handle = capi.peer_alloc(4 * 6 * 8)
+    assert len(handle) == 64 and ptr != 0
+    t = torch.as_tensor(_CudaView(ptr, (4, 6)), device="cuda")
+    t.copy_(torch.arange(24, dtype=torch.float64, device="cuda").reshape(4, 6))
+    assert t.data_ptr() == ptr and float(t.sum()) == 276.0
+    del t
+    capi.peer_free(ptr)
