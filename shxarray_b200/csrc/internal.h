@@ -45,7 +45,9 @@ struct DevTables {
     // nm packing
     const int64_t* slot_src;  // [tri_size*2] index into the user nm list for (slot, cos/sin) or -1
     int nmax, nrows, nlat, nlon, Bp, NC;
-    int GS;               // field-group size of the column order (8, or 4 for tiny batches)
+    int GS;               // field-group size of the column order (8, or 4 for tiny batches): always a power of two
+    int GSH;              // log2(GS): the pack / unpack kernels turn columns into (cos|sin, field) with shifts -- with runtime
+                          // divisions by GS they were integer-instruction bound, not memory bound (r02)
     int Cs, Gs;           // row strides (doubles) of Cm (NC + 2) and G (NC).  The 2 pad columns of Cm make every row start
                           // 16 B mod 64 B, so a CONTIGUOUS block of rows lands in shared memory as a bank-conflict-free padded
                           // tile with a single cp.async.bulk (legendre_tab.cu).  G keeps 128-byte aligned rows: the longitude
@@ -61,6 +63,9 @@ constexpr double POLAR_EPS = 1e-24;
 // Column of (cos/sin cs, field b) inside a Cm / G row: fields come in groups of GS with the cosine and sine part of a
 // group adjacent, [b/GS][cs][b%GS], so that the longitude stage (GS fields per CTA) touches full 128-byte lines.
 __host__ __device__ inline int colidx(int cs, int b, int GS) { return (b / GS) * (2 * GS) + cs * GS + (b % GS); }
+// the same with the shift, and its inverse: column c -> (cs, b)
+__host__ __device__ inline int colidx_sh(int cs, int b, int gsh) { return ((b >> gsh) << (gsh + 1)) + (cs << gsh) + (b & ((1 << gsh) - 1)); }
+__host__ __device__ inline void col_to_field(int c, int gsh, int& cs, int& b) { cs = (c >> gsh) & 1; b = ((c >> (gsh + 1)) << gsh) + (c & ((1 << gsh) - 1)); }
 
 struct Plan;
 

@@ -656,7 +656,11 @@ static int launch_syn3p(const Plan& p, int batch, double* grid, int64_t gs_b, in
     return 0;
 }
 // length, R0, R1, R2, fields per CTA, threads per transform of the persistent synthesis kernel (512 threads, one CTA per SM)
-#define SHB_FFT3P_CONFIGS(X) X(1152, 8, 12, 12, 4, 128) X(1440, 16, 10, 9, 4, 128) X(1536, 16, 16, 6, 4, 128)
+// Three warps per transform: the 96 radix-16 butterflies of a K = 1536 pass (96 / 144 radix-12 / -8 ones at 1152, 90 / 144 / 160 at
+// 1440) then occupy every thread; with four warps a quarter of the threads idled through two of the three passes and ptxas
+// was held to 128 registers (cfg3 synthesis stage 0.324 -> 0.297 ms at 384 threads x 162 registers).  SHB200_FFT3P_TPT=128: r02a shape.
+#define SHB_FFT3P_CONFIGS(X) X(1152, 8, 12, 12, 4, 96) X(1440, 16, 10, 9, 4, 96) X(1536, 16, 16, 6, 4, 96)
+#define SHB_FFT3P_CONFIGS_128(X) X(1152, 8, 12, 12, 4, 128) X(1440, 16, 10, 9, 4, 128) X(1536, 16, 16, 6, 4, 128)
 
 static bool fft3p_on() {
     static const int v = getenv("SHB200_FFT3P") ? atoi(getenv("SHB200_FFT3P")) : 1;
@@ -667,6 +671,15 @@ static bool fft3p_on() {
 int launch_lon_syn_fft3(const Plan& p, int batch, double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, cudaStream_t st) {
     if (!p.fft3_perm || gs_b == 1) return -1;
     if (fft3p_on() && 2 * p.nmax <= p.K && gs_lon == 1) {
+        static const int tpt = getenv("SHB200_FFT3P_TPT") ? atoi(getenv("SHB200_FFT3P_TPT")) : 96;
+        if (tpt == 128) {
+            switch (p.K) {
+#define X(KK, A, B, C, NF, TPT) case KK: if (p.t.GS == NF) return launch_syn3p<fft3::Cfg<KK, A, B, C, NF, TPT>>(p, batch, grid, gs_b, gs_lat, gs_lon, st); break;
+                SHB_FFT3P_CONFIGS_128(X)
+#undef X
+                default: break;
+            }
+        }
         switch (p.K) {
 #define X(KK, A, B, C, NF, TPT) case KK: if (p.t.GS == NF) return launch_syn3p<fft3::Cfg<KK, A, B, C, NF, TPT>>(p, batch, grid, gs_b, gs_lat, gs_lon, st); break;
             SHB_FFT3P_CONFIGS(X)
@@ -683,6 +696,8 @@ int launch_lon_syn_fft3(const Plan& p, int batch, double* grid, int64_t gs_b, in
 }
 int launch_lon_ana_fft3(const Plan& p, int batch, const double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, cudaStream_t st) {
     if (!p.fft3_perm || gs_b == 1) return -1;
+    // (one CTA of 4 x 96 threads per SM instead of two of 4 x 64, the shape that helped the persistent synthesis kernel, is slower
+    // here: 0.311 -> 0.367 ms at cfg3 -- the two CTAs hide each other's row loads and G stores)
     switch (p.K) {
 #define X(KK, A, B, C, NF, TPT) case KK: return launch_ana3<fft3::Cfg<KK, A, B, C, NF, TPT>>(p, batch, grid, gs_b, gs_lat, gs_lon, st);
         SHB_FFT3_CONFIGS(X)

@@ -330,6 +330,8 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
         p.dscale[w] = (double*)q;
     }
     t.nmax = N; t.nrows = R; t.nlat = d.nlat; t.nlon = d.nlon; t.Bp = p.Bp; t.NC = p.NC; t.GS = fft3_group ? fft3_group : (p.Bp >= 8 ? 8 : 4);
+    t.GSH = t.GS == 8 ? 3 : 2;
+    if (t.GS != 4 && t.GS != 8) { set_error("plan_create: internal error: field group size must be 4 or 8"); return SHB200_EINVAL; }
     t.Cs = p.NC + 2; t.Gs = p.NC; t.phase_unit = (p.lon_fft && lon0 == 0.0) ? 1 : 0; t.pt_base = nullptr; t.RT32 = 0; t.m0 = 0; t.mstride = 1; t.first_blk = nullptr;
 
     void* ptr;
