@@ -200,3 +200,38 @@ def test_host_layout_gather_scatter_only_touch_owned_elements():
     ds = info[7:10]
     idx = np.indices(b.shape).reshape(3, -1)
     assert info[3] == 0 and np.array_equal(dense[(idx * ds[:, None]).sum(axis=0)], b.reshape(-1))
+
+
+def test_affinity_helpers_parse_and_degrade():
+    """shxarray_b200.affinity: cpulist parsing, and binding is a described no-op where the device-local CPU list is unknown
+    (this container has no GPU) -- it must never raise or shrink the affinity to nothing."""
+    import os
+    from shxarray_b200 import affinity
+    assert affinity._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert affinity._parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    info = affinity.bind_to_device_numa(0)
+    assert isinstance(info, dict) and "bound" in info and "reason" in info
+    assert os.sched_getaffinity(0) and os.sched_getaffinity(0) <= before
+    os.sched_setaffinity(0, before)
+
+
+def test_plan_cache_digest_memo_sees_in_place_changes():
+    """engine._digest memoises small coordinate arrays per object but verifies the contents: an array changed in place, or a new
+    array at a recycled id(), must give a new digest (a stale one would silently reuse a plan made for another grid)."""
+    import numpy as np
+    from shxarray_b200.engine import _digest
+    lon = np.arange(0.0, 360.0, 1.0)
+    lat = np.arange(-89.5, 90.0, 1.0)
+    d0 = _digest(lat, lon, None)
+    assert _digest(lat, lon, None) == d0 and _digest(lat.copy(), lon.copy(), None) == d0
+    lon[17] += 1e-9
+    d1 = _digest(lat, lon, None)
+    assert d1 != d0
+    lon[17] -= 1e-9
+    assert _digest(lat, lon, None) in (d0, d1)                   # back to the old value bit for bit, or not: never a third state
+    assert _digest(lat, lon.astype(np.float32), None) != d0       # dtype is part of the key
+    big = np.arange(200000, dtype=np.int32)
+    e0 = _digest(big)
+    big[123456] += 1
+    assert _digest(big) != e0

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""A/B of the chained row-tile split of k_leg_ana_small (SHB200_ANA_SPLIT = 0 / 1 / unset) on ONE GPU: analysis of one nmax-2160
+"""A/B of the row-tile split of k_leg_ana_small (SHB200_ANA_SPLIT = 0 never / 1 always / unset: when the orders underfill the GPU) on ONE GPU: analysis of one nmax-2160
 field on the 5' grid, unsharded and as the order shards (r, 8) an 8-GPU run gives each rank; device time per call and a
 checksum of the result bits (the split must not change a bit).
     SHB200_ANA_SPLIT=0 python tools/ab_ana_split.py ; SHB200_ANA_SPLIT=1 python tools/ab_ana_split.py"""
@@ -43,7 +43,6 @@ def timed(fn, reps=5):
 res = {"SHB200_ANA_SPLIT": os.environ.get("SHB200_ANA_SPLIT", "unset"), "nmax": nmax}
 cases = (("unsharded", None), ("shard_0_of_8", (0, 8)), ("shard_7_of_8", (7, 8)), ("shard_1_of_4", (1, 4)), ("shard_1_of_2", (1, 2)))
 only = os.environ.get("CASES")
-res["SHB200_ANA_SPLIT_PUB"] = os.environ.get("SHB200_ANA_SPLIT_PUB", "unset")
 for tag, shard in cases:
     if only and tag not in only.split(","):
         continue
