@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <functional>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -104,7 +105,33 @@ bool points_fused_wanted(int npoints);
 void launch_syn_points(const Plan& p, int batch, double* out, int64_t gs_b, int64_t gs_pt, cudaStream_t st);
 void lon_fft3_perm(int K, std::vector<int>& perm);
 
+// CUDA-graph replay of the launch sequence of small (launch-latency-bound) transforms: plan.cu, "graphs".
+struct GraphKey {
+    int kind = 0, batch = 0, shard_rank = 0, shard_world = 1;
+    uint64_t serial[3] = {0, 0, 0};       // plans involved (unique serial numbers, not addresses: a destroyed plan's address is reused)
+    const void* ptr[4] = {nullptr, nullptr, nullptr, nullptr};
+    int64_t stride[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    bool operator==(const GraphKey& o) const {
+        if (kind != o.kind || batch != o.batch || shard_rank != o.shard_rank || shard_world != o.shard_world) return false;
+        for (int i = 0; i < 3; ++i) if (serial[i] != o.serial[i]) return false;
+        for (int i = 0; i < 4; ++i) if (ptr[i] != o.ptr[i]) return false;
+        for (int i = 0; i < 10; ++i) if (stride[i] != o.stride[i]) return false;
+        return true;
+    }
+};
+struct GraphEntry {
+    GraphKey key;
+    cudaGraphExec_t exec = nullptr;
+    std::string trace;
+    bool bad = false;      // capture failed once: always launched directly
+    uint64_t used = 0;     // LRU stamp
+};
+
 struct Plan {
+    uint64_t serial = 0;
+    std::vector<GraphEntry> graphs;      // owned by the plan the call is "on" (the analysis plan for multiply / apply_mask)
+    cudaStream_t cap_stream = nullptr;
+    uint64_t graph_clock = 0;
     int device = 0, nmax = 0, maxB = 0, Bp = 0, NC = 0;
     int mode = 0, nlat = 0, nlon = 0, quadrature = 0, flags = 0;
     int nrows = 0;
@@ -165,7 +192,15 @@ inline void trace_kernel(const Plan& p, const char* name) {
 struct CallOpts {
     int shard_rank = 0, shard_world = 1;
     const double* degree_scale = nullptr;   // host, nmax+1
+    bool no_events = false;                 // internal: launch sequence under stream capture (the workspace hand-over events stay outside the graph)
 };
+// graphs (plan.cu)
+bool graph_eligible(const Plan& p, const CallOpts& o);
+void drop_graphs(Plan& p);
+// Runs `body(stream, opts_no_events)` directly, or -- from the second call with the same key on -- as a captured graph replayed on
+// `st`.  `touched`: the plans whose workspaces the sequence uses (hand-over events are handled here when the graph is replayed).
+int run_graphed(Plan& owner, const GraphKey& key, cudaStream_t st, Plan* const* touched, int ntouched,
+                const std::function<int(cudaStream_t, bool)>& body);
 int parse_opts(const Plan& p, const shb200_call_opts* o, CallOpts& out);
 // Device-pointer transforms without locking (the caller holds p.mu): used by the public entry points, the host entry
 // points and shb200_multiply.

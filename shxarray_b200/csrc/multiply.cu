@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(256) k_mask_mul(double* __restrict__ g, const 
 
 static int grow_mul_grid(Plan& pc, int64_t need) {
     if (pc.mul_grid_elems < need) {
-        if (pc.mul_grid) { SHB_CUDA(cudaDeviceSynchronize()); cudaFree(pc.mul_grid); }
+        if (pc.mul_grid) { SHB_CUDA(cudaDeviceSynchronize()); cudaFree(pc.mul_grid); drop_graphs(pc); }
         pc.mul_grid = nullptr; pc.mul_grid_elems = 0;
         SHB_CUDA(cudaMalloc((void**)&pc.mul_grid, sizeof(double) * need));
         pc.mul_grid_elems = need;
@@ -62,9 +62,22 @@ extern "C" int shb200_apply_mask(shb200_plan* syn, shb200_plan* ana, int32_t bat
     const int64_t per = (int64_t)pc.nlat * pc.nlon, n = per * batch;
     if ((rc = grow_mul_grid(pc, n))) return rc;
     double* g = pc.mul_grid;
-    if ((rc = do_synthesis(pa, batch, coef, cs_b, cs_nm, g, per, pc.nlon, 1, st, oa))) return rc;
-    k_mask_mul<<<(unsigned)((per + 255) / 256), 256, 0, st>>>(g, mask, pc.nlat, pc.nlon, ms_lat, ms_lon, per, batch);
-    return do_analysis(pc, batch, g, per, pc.nlon, 1, coef_out, os_b, os_nm, st, oc);
+    auto body = [&](cudaStream_t s, bool capturing) {
+        CallOpts a = oa, c = oc;
+        a.no_events = c.no_events = capturing;
+        int r;
+        if ((r = do_synthesis(pa, batch, coef, cs_b, cs_nm, g, per, pc.nlon, 1, s, a))) return r;
+        k_mask_mul<<<(unsigned)((per + 255) / 256), 256, 0, s>>>(g, mask, pc.nlat, pc.nlon, ms_lat, ms_lon, per, batch);
+        return do_analysis(pc, batch, g, per, pc.nlon, 1, coef_out, os_b, os_nm, s, c);
+    };
+    if (graph_eligible(pa, oa) && graph_eligible(pc, oc)) {      // the sea-level iteration calls this with the same buffers every time
+        GraphKey k;
+        k.kind = 3; k.batch = batch; k.serial[0] = pa.serial; k.serial[1] = pc.serial; k.shard_rank = oc.shard_rank; k.shard_world = oc.shard_world;
+        k.ptr[0] = coef; k.ptr[1] = mask; k.ptr[2] = coef_out; k.ptr[3] = g;
+        k.stride[0] = cs_b; k.stride[1] = cs_nm; k.stride[2] = ms_lat; k.stride[3] = ms_lon; k.stride[4] = os_b; k.stride[5] = os_nm;
+        return run_graphed(pc, k, st, uniq, (int)(end - uniq), body);
+    }
+    return body(st, false);
 }
 
 extern "C" int shb200_multiply(shb200_plan* syn_a, shb200_plan* syn_b, shb200_plan* ana, int32_t batch,
@@ -92,10 +105,22 @@ extern "C" int shb200_multiply(shb200_plan* syn_a, shb200_plan* syn_b, shb200_pl
     { int rcg = grow_mul_grid(pc, 2 * n); if (rcg) return rcg; }
     double* ga = pc.mul_grid;
     double* gb = pc.mul_grid + n;
-    const CallOpts none;
-    int rc;
-    if ((rc = do_synthesis(pa, batch, coef_a, as_b, as_nm, ga, per, pc.nlon, 1, st, none))) return rc;
-    if ((rc = do_synthesis(pb, batch, coef_b, bs_b, bs_nm, gb, per, pc.nlon, 1, st, none))) return rc;
-    k_pointwise_mul<<<148 * 8, 256, 0, st>>>(ga, gb, n);
-    return do_analysis(pc, batch, ga, per, pc.nlon, 1, coef_out, os_b, os_nm, st, none);
+    auto body = [&](cudaStream_t s, bool capturing) {
+        CallOpts none;
+        none.no_events = capturing;
+        int r;
+        if ((r = do_synthesis(pa, batch, coef_a, as_b, as_nm, ga, per, pc.nlon, 1, s, none))) return r;
+        if ((r = do_synthesis(pb, batch, coef_b, bs_b, bs_nm, gb, per, pc.nlon, 1, s, none))) return r;
+        k_pointwise_mul<<<148 * 8, 256, 0, s>>>(ga, gb, n);
+        return do_analysis(pc, batch, ga, per, pc.nlon, 1, coef_out, os_b, os_nm, s, none);
+    };
+    const CallOpts plain;
+    if (graph_eligible(pa, plain) && graph_eligible(pb, plain) && graph_eligible(pc, plain)) {      // ten launches -> one graph launch
+        GraphKey k;
+        k.kind = 4; k.batch = batch; k.serial[0] = pa.serial; k.serial[1] = pb.serial; k.serial[2] = pc.serial;
+        k.ptr[0] = coef_a; k.ptr[1] = coef_b; k.ptr[2] = coef_out; k.ptr[3] = ga;
+        k.stride[0] = as_b; k.stride[1] = as_nm; k.stride[2] = bs_b; k.stride[3] = bs_nm; k.stride[4] = os_b; k.stride[5] = os_nm;
+        return run_graphed(pc, k, st, uniq, (int)(end - uniq), body);
+    }
+    return body(st, false);
 }

@@ -9,6 +9,7 @@
 //   alpha = weight*cos(lat*(pi/180))     analysis.pyx:121,129
 // and decides the execution plan: mirror-latitude pairing, FFT vs dense longitude stage, kernel family.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -398,6 +399,8 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
 }
 
 static void free_plan(Plan& p) {
+    drop_graphs(p);
+    if (p.cap_stream) { cudaStreamDestroy(p.cap_stream); p.cap_stream = nullptr; }
     cudaSetDevice(p.device);
     free_host_io(p);
     for (void* d : p.owned) cudaFree(d);
@@ -432,6 +435,7 @@ struct CallScope {
     Plan& p;
     int Bp0, NC0;
     cudaStream_t st;
+    bool events = true;
     CallScope(Plan& plan, int batch, cudaStream_t stream, const CallOpts& o, int which) : p(plan), Bp0(plan.Bp), NC0(plan.NC), st(stream) {
         if (p.Bp > 8) {
             const int bp = std::min(p.Bp, (batch + 7) / 8 * 8);
@@ -439,7 +443,8 @@ struct CallScope {
         }
         p.t.m0 = which == 1 ? o.shard_rank : 0;
         p.t.mstride = which == 1 ? o.shard_world : 1;
-        if (p.has_last && p.last_stream != st) cudaStreamWaitEvent(st, p.ev_done, 0);
+        events = !o.no_events;
+        if (events && p.has_last && p.last_stream != st) cudaStreamWaitEvent(st, p.ev_done, 0);
         p.dscale_on[0] = p.dscale_on[1] = false;
         if (o.degree_scale) {
             // pageable source: the runtime stages the nmax+1 values before returning, so the caller's array is free again
@@ -449,13 +454,99 @@ struct CallScope {
         p.trace.clear();
     }
     ~CallScope() {
-        cudaEventRecord(p.ev_done, st);
-        p.last_stream = st; p.has_last = true;
+        if (events) {
+            cudaEventRecord(p.ev_done, st);
+            p.last_stream = st; p.has_last = true;
+        }
         p.Bp = Bp0; p.NC = NC0; p.t.Bp = Bp0; p.t.NC = NC0;
         p.t.m0 = 0; p.t.mstride = 1;
         p.dscale_on[0] = p.dscale_on[1] = false;
     }
 };
+
+// ---- CUDA graphs for launch-latency-bound transforms ------------------------------------------------------------------
+// BASELINE configs 1 and 5 (nmax 60 / 256, one to four fields) and the spectral products of the sea-level iteration are three to
+// ten kernels of 7-40 us each: their cost is launch latency, not work.  The second call with the same arguments (same plan(s),
+// batch, pointers, strides, order shard) on a small plan captures its launch sequence on a private stream
+// (cudaStreamCaptureModeThreadLocal) and instantiates it; from then on the call is ONE cudaGraphLaunch on the caller's stream.
+// The first call runs directly: it performs every first-use initialisation (function attributes, scratch allocations) that
+// must not happen under capture.  Calls with a fused degree scale (a host array read at call time), timed plans
+// (SHB200_FLAG_TIMING) and large plans are never captured; SHB200_GRAPHS=0 switches the mechanism off.
+static bool graphs_on() {
+    static const bool v = [] { const char* e = getenv("SHB200_GRAPHS"); return !e || atoi(e) != 0; }();
+    return v;
+}
+
+bool graph_eligible(const Plan& p, const CallOpts& o) {
+    if (!graphs_on() || (p.flags & SHB200_FLAG_TIMING) || o.degree_scale || o.no_events) return false;
+    const int64_t nfull = (int64_t)(p.nmax + 1) * (p.nmax + 1);
+    return nfull * p.Bp <= ((int64_t)1 << 21) && (int64_t)p.nlat * (p.mode == SHB200_MODE_POINTS ? 1 : p.nlon) * p.Bp <= ((int64_t)1 << 23);
+}
+
+void drop_graphs(Plan& p) {
+    for (GraphEntry& e : p.graphs)
+        if (e.exec) cudaGraphExecDestroy(e.exec);
+    p.graphs.clear();
+}
+
+int run_graphed(Plan& owner, const GraphKey& key, cudaStream_t st, Plan* const* touched, int ntouched,
+                const std::function<int(cudaStream_t, bool)>& body) {
+    GraphEntry* e = nullptr;
+    for (GraphEntry& g : owner.graphs)
+        if (g.key == key) { e = &g; break; }
+    if (!e) {
+        if (owner.graphs.size() >= 16) {      // least recently used entry makes room
+            size_t old = 0;
+            for (size_t i = 1; i < owner.graphs.size(); ++i)
+                if (owner.graphs[i].used < owner.graphs[old].used) old = i;
+            if (owner.graphs[old].exec) cudaGraphExecDestroy(owner.graphs[old].exec);
+            owner.graphs.erase(owner.graphs.begin() + old);
+        }
+        GraphEntry fresh;
+        fresh.key = key;
+        fresh.used = ++owner.graph_clock;
+        owner.graphs.push_back(fresh);
+        return body(st, false);               // first call with these arguments: direct
+    }
+    e->used = ++owner.graph_clock;
+    if (e->bad) return body(st, false);
+    if (!e->exec) {
+        if (!owner.cap_stream && cudaStreamCreateWithFlags(&owner.cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+            cudaGetLastError(); e->bad = true; return body(st, false);
+        }
+        if (cudaStreamBeginCapture(owner.cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError(); e->bad = true; return body(st, false);
+        }
+        const int rc = body(owner.cap_stream, true);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(owner.cap_stream, &graph);
+        cudaGraphExec_t exec = nullptr;
+        e = nullptr;                          // the launch sequence may have dropped the plan's graphs (a scratch buffer grew)
+        for (GraphEntry& g : owner.graphs)
+            if (g.key == key) { e = &g; break; }
+        if (!e || rc || ce != cudaSuccess || !graph || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+            cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            if (e) e->bad = true;
+            return body(st, false);
+        }
+        cudaGraphDestroy(graph);
+        e->exec = exec;
+        e->trace = owner.trace;
+    }
+    for (int i = 0; i < ntouched; ++i) {
+        Plan& q = *touched[i];
+        if (q.has_last && q.last_stream != st) cudaStreamWaitEvent(st, q.ev_done, 0);
+    }
+    SHB_CUDA(cudaGraphLaunch(e->exec, st));
+    for (int i = 0; i < ntouched; ++i) {
+        Plan& q = *touched[i];
+        cudaEventRecord(q.ev_done, st);
+        q.last_stream = st; q.has_last = true;
+    }
+    owner.trace = e->trace;
+    return 0;
+}
 
 static int check_batch(const Plan& p, int batch) {
     if (batch < 1 || batch > p.maxB) { set_error("batch must be in [1, max_batch] of the plan"); return SHB200_EINVAL; }
@@ -542,6 +633,8 @@ int shb200_plan_create(const shb200_plan_desc* desc, shb200_plan** out) {
         return SHB200_EINVAL;
     }
     shb200_plan* h = new shb200_plan();
+    static std::atomic<uint64_t> next_serial{1};
+    h->p.serial = next_serial.fetch_add(1);
     int rc = build_plan(*desc, h->p);
     if (rc) { free_plan(h->p); delete h; *out = nullptr; return rc; }
     *out = h;
@@ -577,6 +670,19 @@ int shb200_synthesis(shb200_plan* plan, int32_t batch, const double* coef, int64
     int rc = parse_opts(p, opts, o);
     if (rc) return rc;
     std::lock_guard<std::mutex> lock(p.mu);
+    if (graph_eligible(p, o) && batch >= 1 && batch <= p.maxB) {
+        GraphKey k;
+        k.kind = 1; k.batch = batch; k.serial[0] = p.serial;
+        k.ptr[0] = coef; k.ptr[1] = grid;
+        k.stride[0] = cs_b; k.stride[1] = cs_nm; k.stride[2] = gs_b; k.stride[3] = gs_lat; k.stride[4] = gs_lon;
+        Plan* touched[1] = {&p};
+        SHB_CUDA(cudaSetDevice(p.device));
+        return run_graphed(p, k, (cudaStream_t)stream, touched, 1, [&](cudaStream_t s, bool capturing) {
+            CallOpts oo = o;
+            oo.no_events = capturing;
+            return do_synthesis(p, batch, coef, cs_b, cs_nm, grid, gs_b, gs_lat, gs_lon, s, oo);
+        });
+    }
     return do_synthesis(p, batch, coef, cs_b, cs_nm, grid, gs_b, gs_lat, gs_lon, (cudaStream_t)stream, o);
 }
 
@@ -588,6 +694,19 @@ int shb200_analysis(shb200_plan* plan, int32_t batch, const double* grid, int64_
     int rc = parse_opts(p, opts, o);
     if (rc) return rc;
     std::lock_guard<std::mutex> lock(p.mu);
+    if (graph_eligible(p, o) && p.quadrature != SHB200_QUAD_NONE && batch >= 1 && batch <= p.maxB) {
+        GraphKey k;
+        k.kind = 2; k.batch = batch; k.serial[0] = p.serial; k.shard_rank = o.shard_rank; k.shard_world = o.shard_world;
+        k.ptr[0] = grid; k.ptr[1] = coef;
+        k.stride[0] = gs_b; k.stride[1] = gs_lat; k.stride[2] = gs_lon; k.stride[3] = cs_b; k.stride[4] = cs_nm;
+        Plan* touched[1] = {&p};
+        SHB_CUDA(cudaSetDevice(p.device));
+        return run_graphed(p, k, (cudaStream_t)stream, touched, 1, [&](cudaStream_t s, bool capturing) {
+            CallOpts oo = o;
+            oo.no_events = capturing;
+            return do_analysis(p, batch, grid, gs_b, gs_lat, gs_lon, coef, cs_b, cs_nm, s, oo);
+        });
+    }
     return do_analysis(p, batch, grid, gs_b, gs_lat, gs_lon, coef, cs_b, cs_nm, (cudaStream_t)stream, o);
 }
 

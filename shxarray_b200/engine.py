@@ -552,11 +552,12 @@ class SHEngine:
         return grid_out, out
 
     # ------------------------------------------------------------------------------------------
-    def multiply(self, coef_a, nmax_a, coef_b, nmax_b):
+    def multiply(self, coef_a, nmax_a, coef_b, nmax_b, out=None):
         """Product of two SH fields through the spatial domain, kept on the device (shtns.py:394-420):
         Gauss grid of nmax_a+nmax_b, two syntheses, pointwise product, Gauss-quadrature analysis.
         coef_a [B, (nmax_a+1)^2], coef_b [B, (nmax_b+1)^2] full triangles in nm order; torch CUDA tensors or numpy.
-        Returns [B, (nmax_a+nmax_b+1)^2]."""
+        Returns [B, (nmax_a+nmax_b+1)^2]; ``out`` (torch CUDA, that shape): written in place -- a loop that calls this with the
+        same input and output tensors (the sea-level iteration) replays one captured CUDA graph per call instead of ten launches."""
         import torch
         nmax = int(nmax_a) + int(nmax_b)
         lon, lat, lw = _gauss_grid_cached(nmax)
@@ -573,7 +574,10 @@ class SHEngine:
         pc = self.get_plan(nmax, lat, lon, B, quadrature=capi.QUAD_LATWEIGHTS, weight=1.0 / (2.0 * len(lon)), lat_weights=lw)
         pa = self.get_plan(int(nmax_a), lat, lon, B, n=na, m=ma)
         pb = pa if nmax_a == nmax_b else self.get_plan(int(nmax_b), lat, lon, B, n=nb_, m=mb)
-        out = torch.empty((B, (nmax + 1) ** 2), dtype=torch.float64, device=dev)
+        if out is None or host:
+            out = torch.empty((B, (nmax + 1) ** 2), dtype=torch.float64, device=dev)
+        elif tuple(out.shape) != (B, (nmax + 1) ** 2) or str(out.dtype) != "torch.float64" or not out.is_cuda:
+            raise ValueError("multiply: out must be a float64 CUDA tensor of shape [B, (nmax_a+nmax_b+1)^2]")
         stream = torch.cuda.current_stream(dev).cuda_stream
         step = min(pa.max_batch, pb.max_batch, pc.max_batch)
         for b0 in range(0, B, step):

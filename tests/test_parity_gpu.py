@@ -1076,3 +1076,41 @@ def test_push_rows_and_peer_allocation_single_gpu():
     assert t.data_ptr() == ptr and float(t.sum()) == 276.0
     del t
     capi.peer_free(ptr)
+
+
+@pytest.mark.gpu
+def test_cuda_graph_replay_of_small_transforms_follows_the_data(engine):
+    """Small (launch-latency-bound) plans replay a captured CUDA graph from the third identical call on (plan.cu: run_graphed;
+    the first call runs directly, the second captures).  A replay must read the CURRENT contents of the same buffers, give bit
+    for bit what the direct launch gives, keep the kernel trace, and a call with other buffers must not hit the same graph."""
+    import torch
+    nmax, B = 40, 3
+    g = sb.lonlat_grid(nmax, gtype="gauss")
+    lon, lat = g["lon"], g["lat"]
+    c = torch.from_numpy(S.random_coefficients(nmax, B, kaula=False, seed=3)).cuda()
+    f = torch.empty((B, len(lat), len(lon)), dtype=torch.float64, device="cuda")
+    a = torch.empty_like(c)
+    ref_f = engine.synthesis(c, lon=lon, lat=lat, nmax=nmax).clone()                   # other output buffer: direct launch
+    ref_a = engine.analysis(ref_f, nmax, lon, lat, quadrature="gauss").clone()
+    for it in range(5):                                                              # same buffers: direct, capture, replay x3
+        engine.synthesis(c, lon=lon, lat=lat, nmax=nmax, out=f)
+        engine.analysis(f, nmax, lon, lat, quadrature="gauss", out=a)
+        assert torch.equal(f, ref_f) and torch.equal(a, ref_a), it
+    plan = [p for p in engine._plans.values() if p.nmax == nmax][-1]
+    assert plan.last_kernels()[-1].startswith("k_unpack")                              # trace survives the replay
+    c2 = torch.from_numpy(S.random_coefficients(nmax, B, kaula=False, seed=4)).cuda()
+    want_f = engine.synthesis(c2, lon=lon, lat=lat, nmax=nmax).clone()
+    c.copy_(c2)                                                                        # new data in the SAME input buffer
+    engine.synthesis(c, lon=lon, lat=lat, nmax=nmax, out=f)
+    engine.analysis(f, nmax, lon, lat, quadrature="gauss", out=a)
+    assert torch.equal(f, want_f)
+    assert float(((a - c2).abs().amax(dim=1) / c2.abs().amax(dim=1)).max()) < 1e-12
+    # the fused spectral product (ten launches) replays as one graph too
+    x = torch.from_numpy(S.random_coefficients(12, 2, kaula=False, seed=5)).cuda()
+    y = torch.from_numpy(S.random_coefficients(9, 2, kaula=False, seed=6)).cuda()
+    outs = [engine.multiply(x, 12, y, 9).clone() for _ in range(4)]
+    out_buf = torch.empty_like(outs[0])
+    for it in range(4):
+        engine.multiply(x, 12, y, 9, out=out_buf)
+        assert torch.equal(out_buf, outs[0]), it
+    assert all(torch.equal(o, outs[0]) for o in outs)
