@@ -425,22 +425,45 @@ static int run_host_call(HostCall& c) {
         if ((rc = ensure_stage(h, out_stage, c.out.full.total))) return rc;
         c.in.dev = h.stage[in_stage]; c.out.dev = h.stage[out_stage];
     }
-    int nchunk = host_chunks(c.batch);
-    if (!(c.in.batch_outer && c.out.batch_outer && (!rt || c.mid.batch_outer))) nchunk = 1;
-    const int per = nchunk == 1 ? c.batch : ((c.batch + nchunk - 1) / nchunk + 7) / 8 * 8;         // whole groups of 8 fields per chunk
-    nchunk = (c.batch + per - 1) / per;
+    // chunk sizes: up to 4 equal chunks of whole 8-field groups; the chunk at the exposed end of the pipeline -- the FIRST of a
+    // synthesis (nothing travels back before its grid exists), the LAST of an analysis (its coefficients travel back after
+    // everything else), both for the round trip -- is cut into 8 + 8 + rest fields, which shortens the un-overlapped head /
+    // tail of the call (SHB200_HOST_EDGE_SPLIT=0: equal chunks only)
+    std::vector<int> nbs;
+    {
+        int nchunk = host_chunks(c.batch);
+        if (!(c.in.batch_outer && c.out.batch_outer && (!rt || c.mid.batch_outer))) nchunk = 1;
+        const int per = nchunk == 1 ? c.batch : ((c.batch + nchunk - 1) / nchunk + 7) / 8 * 8;
+        for (int b0 = 0; b0 < c.batch; b0 += per) nbs.push_back(std::min(per, c.batch - b0));
+        static const bool edge_split = [] { const char* e = getenv("SHB200_HOST_EDGE_SPLIT"); return !e || atoi(e) != 0; }();
+        auto split = [&](size_t at, bool small_first) {
+            const int nb = nbs[at];
+            if (nb < 16) return;
+            std::vector<int> parts;
+            if (nb >= 24) parts = small_first ? std::vector<int>{8, 8, nb - 16} : std::vector<int>{nb - 16, 8, 8};
+            else parts = small_first ? std::vector<int>{8, nb - 8} : std::vector<int>{nb - 8, 8};
+            nbs.erase(nbs.begin() + at);
+            nbs.insert(nbs.begin() + at, parts.begin(), parts.end());
+        };
+        if (edge_split && nbs.size() > 1) {
+            if (c.which == 1 || rt) split(nbs.size() - 1, false);
+            if (c.which == 0 || rt) split(0, true);
+        }
+    }
+    const int nchunk = (int)nbs.size();        // <= 4 + 2 + 2 = HostIO::MAXCH
+    // an 8-field chunk of a tensor-core plan runs 32 columns wide (half of them zero): it stays on the kernels of its neighbours
+    if (p.dmma && p.Bp >= 16) c.o_syn.min_fields = c.o_ana.min_fields = 16;
+    std::vector<int> b0s(nchunk, 0);
+    for (int k = 1; k < nchunk; ++k) b0s[k] = b0s[k - 1] + nbs[k - 1];
 
     std::vector<ChunkView> vin(nchunk), vmid(rt ? nchunk : 0), vout(nchunk);
-    std::vector<int> nbs(nchunk);
     for (int k = 0; k < nchunk; ++k) {
-        const int b0 = k * per, nb = std::min(per, c.batch - b0);
-        nbs[k] = nb;
-        vin[k] = chunk_view(c.in, b0, nb);
-        vout[k] = chunk_view(c.out, b0, nb);
-        if (rt) vmid[k] = chunk_view(c.mid, b0, nb);
+        vin[k] = chunk_view(c.in, b0s[k], nbs[k]);
+        vout[k] = chunk_view(c.out, b0s[k], nbs[k]);
+        if (rt) vmid[k] = chunk_view(c.mid, b0s[k], nbs[k]);
     }
     auto is_direct = [&](const HostArray& a) {
-        for (int k = 0; k < nchunk; ++k) if (!(a.pinned && direct_ok(chunk_view(a, k * per, nbs[k]).L))) return false;
+        for (int k = 0; k < nchunk; ++k) if (!(a.pinned && direct_ok(chunk_view(a, b0s[k], nbs[k]).L))) return false;
         return true;
     };
     const bool out_direct = is_direct(c.out);

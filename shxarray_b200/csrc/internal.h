@@ -92,7 +92,7 @@ void launch_unpack(const Plan& p, int batch, double* coef, int64_t cs_b, int64_t
 void launch_pack_shard(const Plan& p, int batch, double* packed, int64_t ps_b, cudaStream_t st);   // shard.cu
 // Legendre stage
 void launch_legendre_syn(const Plan& p, cudaStream_t st);   // Cm -> G
-void launch_legendre_ana(const Plan& p, cudaStream_t st);   // G  -> Cm
+bool launch_legendre_ana(const Plan& p, cudaStream_t st);   // G  -> Cm
 // longitude stage
 int launch_lon_syn(const Plan& p, int batch, double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, cudaStream_t st);
 int launch_lon_ana(const Plan& p, int batch, const double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, cudaStream_t st);
@@ -192,6 +192,7 @@ inline void trace_kernel(const Plan& p, const char* name) {
 struct CallOpts {
     int shard_rank = 0, shard_world = 1;
     const double* degree_scale = nullptr;   // host, nmax+1
+    int min_fields = 0;                     // internal: effective width of the call is at least this many fields (host pipeline: 8-field edge chunks)
     bool no_events = false;                 // internal: launch sequence under stream capture (the workspace hand-over events stay outside the graph)
 };
 // graphs (plan.cu)

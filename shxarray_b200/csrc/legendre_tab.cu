@@ -459,7 +459,7 @@ static bool launch_ana_tab_ncq(const Plan& p, cudaStream_t st) {
 }
 
 bool launch_legendre_ana_tab(const Plan& p, cudaStream_t st) {
-    if (!p.Ptab || p.NC < 32) return false;
+    if (!p.Ptab || p.NC < 32 || p.nrows > 8192) return false;      // s0_s[256]: skip schedule of up to 256 row tiles
     if (p.NC <= 32) return launch_ana_tab_ncq<1>(p, st);
     if (p.NC <= 64) return launch_ana_tab_ncq<2>(p, st);
     return launch_ana_tab_ncq<4>(p, st);

@@ -225,10 +225,6 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
     }
     p.nrows = (int)i1.size();
     const int R = p.nrows;
-    if (d.quadrature != SHB200_QUAD_NONE && R > 8192) {
-        set_error("plan_create: analysis supports at most 8192 distinct latitude rows (recursion state is kept in shared memory)");
-        return SHB200_EUNSUPPORTED;
-    }
     std::vector<double> cost(R), w1(R, 0.0), w2(R, 0.0);
     for (int r = 0; r < R; ++r) cost[r] = cost_lat[i1[r]];
     if (d.quadrature != SHB200_QUAD_NONE) {
@@ -438,7 +434,7 @@ struct CallScope {
     bool events = true;
     CallScope(Plan& plan, int batch, cudaStream_t stream, const CallOpts& o, int which) : p(plan), Bp0(plan.Bp), NC0(plan.NC), st(stream) {
         if (p.Bp > 8) {
-            const int bp = std::min(p.Bp, (batch + 7) / 8 * 8);
+            const int bp = std::min(p.Bp, std::max((batch + 7) / 8 * 8, o.min_fields));
             p.Bp = bp; p.NC = 2 * bp; p.t.Bp = bp; p.t.NC = 2 * bp;
         }
         p.t.m0 = which == 1 ? o.shard_rank : 0;
@@ -589,7 +585,7 @@ int do_analysis(Plan& p, int batch, const double* grid, int64_t gs_b, int64_t gs
     rc = launch_lon_ana(p, batch, grid, gs_b, gs_lat, gs_lon, st);
     if (rc) return rc;
     if (tm) cudaEventRecord(p.ev[5], st);
-    launch_legendre_ana(p, st);
+    if (!launch_legendre_ana(p, st)) { set_error("analysis: out of device memory for the recursion state of a grid with more than 8192 latitude rows"); return SHB200_ENOMEM; }
     if (tm) cudaEventRecord(p.ev[6], st);
     launch_unpack(p, batch, coef, cs_b, cs_nm, st);
     if (tm) { cudaEventRecord(p.ev[7], st); p.timed_ana = true; }
@@ -610,7 +606,7 @@ int do_analysis_packed(Plan& p, int batch, const double* grid, int64_t gs_b, int
     rc = launch_lon_ana(p, batch, grid, gs_b, gs_lat, gs_lon, st);
     if (rc) return rc;
     if (tm) cudaEventRecord(p.ev[5], st);
-    launch_legendre_ana(p, st);
+    if (!launch_legendre_ana(p, st)) { set_error("analysis: out of device memory for the recursion state of a grid with more than 8192 latitude rows"); return SHB200_ENOMEM; }
     if (tm) cudaEventRecord(p.ev[6], st);
     launch_pack_shard(p, batch, packed, ps_b, st);
     if (tm) { cudaEventRecord(p.ev[7], st); p.timed_ana = true; }

@@ -1114,3 +1114,27 @@ def test_cuda_graph_replay_of_small_transforms_follows_the_data(engine):
         engine.multiply(x, 12, y, 9, out=out_buf)
         assert torch.equal(out_buf, outs[0]), it
     assert all(torch.equal(o, outs[0]) for o in outs)
+
+
+@pytest.mark.parametrize("B,flags", [(2, 0), (16, 0), (3, capi.FLAG_NO_DMMA)])
+def test_analysis_of_grids_with_more_than_8192_latitude_rows(B, flags):
+    """The reference loops over any number of latitudes (analysis.pyx:121-139).  Analysis kernels that keep the recursion state
+    of all rows in shared memory hold 8192 rows; taller grids (no mirror pairs here: 9001 distinct rows) keep that state in
+    a per-CTA slice of a global scratch array (k_leg_ana_dfma) or run row tiles (k_leg_ana_small).  Compared with the oracle
+    on a subset of fields; the synthesis of the same plan is checked too."""
+    nmax = 12
+    lat = -70.0 + 1.0 / 256 + np.arange(9001) / 64.0          # exactly equidistant (analysis.pyx:57-60 demands it), no latitude has its mirror
+    lon = np.arange(0.0, 360.0, 11.25)
+    f = np.random.default_rng(77).standard_normal((B, len(lat), len(lon)))
+    eng = sb.SHEngine(0, flags=flags)
+    a = eng.analysis(f, nmax, lon, lat, quadrature="shlib")
+    plan = [p for p in eng._plans.values()][-1]
+    assert plan.last_kernels()[1] in (("k_leg_ana_dfma",) if (B == 16 or flags) else ("k_leg_ana_small",)), plan.last_kernels()
+    nb = min(B, 2)
+    aref = O.analysis(f[:nb], nmax, lon, lat, kind="port")
+    assert per_field_err(a[:nb], aref) <= TOL
+    n, m = sb.nm_index(nmax)
+    s = eng.synthesis(a, n, m, lon, lat)
+    rows = np.arange(0, len(lat), 997)
+    sref = np.moveaxis(O.synthesis(a[:nb], n, m, lon, lat[rows], kind="port"), 2, 0)
+    assert per_field_err(s[:nb][:, rows], sref) <= TOL
