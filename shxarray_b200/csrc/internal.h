@@ -129,6 +129,7 @@ struct GraphEntry {
 
 struct Plan {
     uint64_t serial = 0;
+    int cur_batch = 0;                   // fields of the call whose launch sequence is being issued (CallScope)
     std::vector<GraphEntry> graphs;      // owned by the plan the call is "on" (the analysis plan for multiply / apply_mask)
     cudaStream_t cap_stream = nullptr;
     uint64_t graph_clock = 0;

@@ -437,6 +437,7 @@ struct CallScope {
             const int bp = std::min(p.Bp, std::max((batch + 7) / 8 * 8, o.min_fields));
             p.Bp = bp; p.NC = 2 * bp; p.t.Bp = bp; p.t.NC = 2 * bp;
         }
+        p.cur_batch = batch;
         p.t.m0 = which == 1 ? o.shard_rank : 0;
         p.t.mstride = which == 1 ? o.shard_world : 1;
         events = !o.no_events;

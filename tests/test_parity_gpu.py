@@ -1001,7 +1001,7 @@ np.savez(sys.argv[2], **out)
 
 @pytest.mark.gpu
 def test_chained_row_tile_split_is_bit_identical(tmp_path):
-    """k_leg_ana_small with its row tiles chained across CTAs (SHB200_ANA_SPLIT=1: what an order shard of a multi-GPU analysis
+    """k_leg_ana_small (and k_leg_ana_one, the single-field kernel) with its row tiles as separate CTAs (SHB200_ANA_SPLIT=1: what an order shard of a multi-GPU analysis
     runs) against the sequential tile loop (=0): the same additions in the same order, so every bit must agree -- unsharded
     and for an order shard, one and three fields (600 latitudes = 300 mirror pairs = several row tiles)."""
     import subprocess
@@ -1013,7 +1013,7 @@ def test_chained_row_tile_split_is_bit_identical(tmp_path):
         res[mode] = np.load(path)
     for key in res["0"].files:
         if key.startswith("k_"):
-            assert "k_leg_ana_small" in str(res["0"][key]), (key, str(res["0"][key]))
+            assert "k_leg_ana_small" in str(res["0"][key]) or "k_leg_ana_one" in str(res["0"][key]), (key, str(res["0"][key]))
             continue
         a0, a1 = res["0"][key], res["1"][key]
         assert np.isfinite(a0).all() and np.abs(a0).max() > 0
@@ -1138,3 +1138,27 @@ def test_analysis_of_grids_with_more_than_8192_latitude_rows(B, flags):
     rows = np.arange(0, len(lat), 997)
     sref = np.moveaxis(O.synthesis(a[:nb], n, m, lon, lat[rows], kind="port"), 2, 0)
     assert per_field_err(s[:nb][:, rows], sref) <= TOL
+
+
+@pytest.mark.parametrize("nmax,gtype,quad", [(150, "regular", "shlib"), (95, "gauss", "gauss")])
+def test_single_field_analysis_kernel_vs_oracle(engine, nmax, gtype, quad):
+    """One live field (BASELINE config 4's shape) runs k_leg_ana_one: contraction on the CUDA cores, four rows per thread, sums
+    over lanes / warps / row tiles in a fixed order.  Against the oracle, against the DMMA tiny-batch kernel (the same field in a
+    call of two), repeated (deterministic), and on a plan made for more fields than the call has."""
+    g = sb.lonlat_grid(nmax, gtype=gtype)
+    lon, lat = g["lon"], g["lat"]
+    if quad == "shlib":
+        f = np.random.default_rng(5).standard_normal((2, len(lat), len(lon)))
+    else:                                              # the oracle integrates with shlib's weights only: exact round trip instead
+        c = S.random_coefficients(nmax, 2, kaula=False, seed=41)
+        f = engine.synthesis(c, lon=lon, lat=lat, nmax=nmax)
+    a1 = engine.analysis(f[:1], nmax, lon, lat, quadrature=quad)
+    plan = [p for p in engine._plans.values() if p.nmax == nmax][-1]
+    assert plan.last_kernels()[1] == "k_leg_ana_one", plan.last_kernels()
+    aref = O.analysis(f[:1], nmax, lon, lat, kind="port") if quad == "shlib" else c[:1]
+    assert per_field_err(a1, aref) <= TOL
+    a2 = engine.analysis(f, nmax, lon, lat, quadrature=quad)           # two fields: k_leg_ana_small
+    assert [p for p in engine._plans.values() if p.nmax == nmax][-1].last_kernels()[1] == "k_leg_ana_small"
+    assert per_field_err(a2[:1], a1) <= 1e-13
+    assert np.array_equal(engine.analysis(f[:1], nmax, lon, lat, quadrature=quad), a1)
+    assert np.array_equal(engine.analysis(f[1:], nmax, lon, lat, quadrature=quad)[0], engine.analysis(np.ascontiguousarray(f[1:]), nmax, lon, lat, quadrature=quad)[0])

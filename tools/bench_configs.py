@@ -60,7 +60,7 @@ if __name__ == "__main__":
     out = []
 
     def add(tag, *a, **k):
-        if not only or any(o in tag for o in only):
+        if not only or any((o[1:] == tag) if o.startswith("=") else (o in tag) for o in only):     # "=tag": exact match
             out.append(run(tag, *a, **k))
 
     add("cfg1 nmax60 shlib 1deg B=1", 60, 1, "regular", "shlib")
@@ -79,4 +79,4 @@ if __name__ == "__main__":
     add("cfg4d nmax2160 5min B=64 (20 GB P table)", 2160, 64, None, "weights", **kw)
     # shlib's own default grid at nmax 2160 (shlib.pyx:87-92: 5760 x 11520): 57 GB P table, longitude length 11520
     add("cfg4e nmax2160 shlib grid 5760x11520 B=16 (57 GB P table)", 2160, 16, "regular", "shlib")
-    json.dump(out, open("gpurun_out/configs_r02.json", "w"), indent=1)
+    json.dump(out, open(os.environ.get("CONFIGS_OUT", "gpurun_out/configs_r02.json"), "w"), indent=1)
