@@ -535,7 +535,7 @@ void lon_fft_perm(int K, int Bp, std::vector<int>& perm) {
 
 // longitude counts with compile-time kernels: regular grids of 1 / 0.5 / 0.25 / 0.125 degree and 5', Gauss grids of
 // nmax 96 ... 2160 (engine.py: _nice_nlon)
-#define SHB_FFT_STATIC_LENGTHS(X) X(240) X(360) X(384) X(480) X(576) X(720) X(768) X(1152) X(1440) X(1536) X(2304) X(2880) X(3072) X(4320) X(4608)
+#define SHB_FFT_STATIC_LENGTHS(X) X(240) X(360) X(384) X(480) X(576) X(720) X(768) X(1152) X(1440) X(1536) X(2304) X(2880) X(3072) X(4320) X(4608) X(5760) X(11520)
 
 template <class FP>
 static int launch_syn_fp(const Plan& p, const FP& fp, int NF, int nthreads, size_t smem, int batch, double* grid, int64_t gs_b, int64_t gs_lat,

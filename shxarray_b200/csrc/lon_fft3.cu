@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(C::NT, 1) k_lon_syn_fft3p(DevTables t, const i
     X(240, 16, 15, 1, 8, 32) X(360, 8, 9, 5, 8, 32) X(384, 8, 8, 6, 8, 32) X(480, 8, 10, 6, 8, 32) X(576, 8, 9, 8, 8, 32)  \
     X(720, 8, 10, 9, 8, 32) X(768, 8, 12, 8, 8, 32) X(1152, 8, 12, 12, 4, 64) X(1440, 16, 10, 9, 4, 64)                    \
     X(1536, 16, 16, 6, 4, 64) X(2304, 16, 12, 12, 4, 128) X(2880, 16, 15, 12, 4, 128) X(3072, 16, 16, 12, 4, 128)          \
-    X(4320, 16, 18, 15, 2, 256) X(4608, 16, 18, 16, 2, 256)
+    X(4320, 16, 18, 15, 2, 256) X(4608, 16, 18, 16, 2, 256) X(5760, 16, 18, 20, 2, 256)
 
 struct Fft3Info { int K, R0, R1, R2, NF, TPT; };
 static const Fft3Info* fft3_find(int K) {

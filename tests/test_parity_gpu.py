@@ -1162,3 +1162,26 @@ def test_single_field_analysis_kernel_vs_oracle(engine, nmax, gtype, quad):
     assert per_field_err(a2[:1], a1) <= 1e-13
     assert np.array_equal(engine.analysis(f[:1], nmax, lon, lat, quadrature=quad), a1)
     assert np.array_equal(engine.analysis(f[1:], nmax, lon, lat, quadrature=quad)[0], engine.analysis(np.ascontiguousarray(f[1:]), nmax, lon, lat, quadrature=quad)[0])
+
+
+@pytest.mark.parametrize("K,kern", [(5760, "fft3"), (11520, "fft<static")])
+def test_long_regular_grid_rows_vs_oracle(engine, K, kern):
+    """Longitude counts of shlib's own regular grids for nmax 513 ... 2160 (shlib.pyx:87-92: 5760 and 11520 points per row):
+    compile-time FFT kernels (three-pass 16 x 18 x 20 for 5760; in-place mixed radix, one transform per CTA, for 11520)."""
+    nmax, B = 40, 16
+    lon = -180.0 + 180.0 / K + np.arange(K) * (360.0 / K)
+    lat = np.array([-89.96875, -45.03125, -0.03125, 0.03125, 45.03125, 89.96875, 12.53125])
+    n, m = sb.nm_index(nmax)
+    c = S.random_coefficients(nmax, B, kaula=False, seed=61)
+    f = engine.synthesis(c, n, m, lon, lat)
+    plan = [p for p in engine._plans.values() if p.nmax == nmax][-1]
+    assert kern in plan.last_kernels()[-1], plan.last_kernels()
+    ref = np.moveaxis(O.synthesis(c[:2], n, m, lon, lat, kind="port"), 2, 0)
+    assert per_field_err(f[:2], ref) <= TOL
+    g = np.random.default_rng(3).standard_normal((B, len(lat), K))
+    lw = np.cos(lat * np.pi / 180)
+    a = engine.analysis(g, nmax, lon, lat, quadrature="weights", lat_weights=lw, weight=1e-3)
+    assert kern in [p for p in engine._plans.values() if p.nmax == nmax][-1].last_kernels()[0]
+    # the oracle's row weight is weight * cos(lat * pi/180) (analysis.pyx:121,129): the same numbers to an ulp
+    aref = O.analysis(g[:1], nmax, lon, lat, kind="port", weight=1e-3)
+    assert per_field_err(a[:1], aref) <= TOL

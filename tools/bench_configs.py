@@ -79,4 +79,6 @@ if __name__ == "__main__":
     add("cfg4d nmax2160 5min B=64 (20 GB P table)", 2160, 64, None, "weights", **kw)
     # shlib's own default grid at nmax 2160 (shlib.pyx:87-92: 5760 x 11520): 57 GB P table, longitude length 11520
     add("cfg4e nmax2160 shlib grid 5760x11520 B=16 (57 GB P table)", 2160, 16, "regular", "shlib")
+    # shlib's own default grid at nmax 1080 (2880 x 5760): longitude length 5760
+    add("cfg6 nmax1080 shlib grid 2880x5760 B=16", 1080, 16, "regular", "shlib")
     json.dump(out, open(os.environ.get("CONFIGS_OUT", "gpurun_out/configs_r02.json"), "w"), indent=1)
