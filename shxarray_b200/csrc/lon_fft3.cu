@@ -222,16 +222,16 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // twiddle tables of this CTA: T1[(q-1)*R0 + k] = W^(k q K/(R0 R1)), T2[k] = W^(k K/(R0 R1 R2)); W = exp(-2 pi i/K) forward,
 // conjugated for the inverse transform
-template <class C, bool INV>
+template <class C, bool INV, int TWS = 1>                         // TWS: the plan's root table belongs to the length TWS * C::K
 __device__ __forceinline__ void fill_tables(const double2* __restrict__ tw, double2* T1, double2* T2, int tid) {
     for (int i = tid; i < C::T1N; i += C::NT) {
         const int q = i / C::R0 + 1, k = i - (q - 1) * C::R0;
-        double2 w = tw[k * q * (C::K / (C::R0 * C::R1))];
+        double2 w = tw[k * q * (C::K / (C::R0 * C::R1)) * TWS];
         if (INV) w.y = -w.y;
         T1[i] = w;
     }
     for (int i = tid; i < C::T2N; i += C::NT) {
-        double2 w = tw[i];                                      // K / (R0 R1 R2) = 1
+        double2 w = tw[i * TWS];                                // K / (R0 R1 R2) = 1
         if (INV) w.y = -w.y;
         T2[i] = w;
     }
@@ -453,6 +453,137 @@ __global__ void __launch_bounds__(C::NT, C::MINB) k_lon_ana_fft3(DevTables t, co
     prof.mark(13);
 }
 
+// ---- rows of length 2 * C::K (shlib's own nmax-2160 grid: 11520 = 2 x 5760) ---------------------------------------------------
+// A transform of that length does not fit the three-pass scheme (radices <= 20) and, alone in the 227 KB of a CTA, ran as six
+// in-place passes (lon_fft.cu: 7x its HBM time).  One radix-2 step by hand instead, two three-pass transforms of length C::K per
+// (latitude pair, field) in one CTA:
+//   synthesis: x[2j] = IDFT_K(X[k] + X[k+K]), x[2j+1] = IDFT_K((X[k] - X[k+K]) w^k), w = exp(2 pi i / 2K).  With 2 nmax < K the
+//     only non-zero bins are k = m and 2K - m, so the even half gets (Wa, Wb) at (m, K - m) like a length-K row and the odd half
+//     (Wa w^m, Wb conj(w^m)); the halves write the even / odd longitudes of the grid row (stride 2 gs_lon);
+//   analysis: E = DFT_K(x[2j]), O = DFT_K(x[2j+1]);  X[m] = E[m] + tw[m] O[m],  X[2K - m] = E[K - m] + conj(tw[m]) O[K - m].
+template <class C>
+__global__ void __launch_bounds__(C::NT, 1) k_lon_syn_fft3s2(DevTables t, const int* __restrict__ perm, int batch, const double* __restrict__ G,
+                                                             double* __restrict__ grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon) {
+    extern __shared__ double2 smem2[];
+    constexpr int K = C::K, NT = C::NT, S = C::S;
+    static_assert(C::NF == 2 && C::NP == 3, "two halves per CTA");
+    double2* T1 = smem2 + (size_t)2 * C::BUF;
+    double2* T2 = T1 + C::T1N;
+    const int N = t.nmax, R = t.nrows;
+    const int row = blockIdx.y, b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int i1 = t.row_i1[row], i2 = t.row_i2[row];
+    const bool mirror = i2 >= 0;
+    fill_tables<C, true, 2>(t.tw, T1, T2, tid);
+    double2* xe = smem2;
+    double2* xo = smem2 + C::BUF;
+    for (int k = N + 1 + tid; k < K - N; k += NT) { const int q = swz<S>(perm[k]); xe[q] = make_double2(0.0, 0.0); xo[q] = make_double2(0.0, 0.0); }
+    const int64_t gstep = (int64_t)R * 2 * t.Gs;
+    const double* gcol = G + ((int64_t)row * 2) * t.Gs + colidx(0, b, t.GS);
+    constexpr int UN = 4;
+    for (int m0 = tid; m0 <= N; m0 += NT * UN) {
+        double Ec[UN], Es[UN], Oc[UN], Os[UN];
+        double2 ph[UN], wm[UN];
+        int pk[UN], pkc[UN];
+        bool ok[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int m = m0 + u * NT;
+            ok[u] = m <= N;
+            if (ok[u]) {
+                const double* g = gcol + (int64_t)m * gstep;
+                Ec[u] = g[0]; Es[u] = g[t.GS]; Oc[u] = g[t.Gs]; Os[u] = g[t.Gs + t.GS];
+                ph[u] = t.phase[m];
+                wm[u] = cconj(t.tw[m]);                                   // exp(+2 pi i m / 2K)
+                pk[u] = perm[m]; pkc[u] = perm[m ? K - m : 0];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            if (!ok[u]) continue;
+            const double A = Ec[u] + Oc[u], B = Es[u] + Os[u];
+            const double Ap = mirror ? Ec[u] - Oc[u] : 0.0, Bp_ = mirror ? Es[u] - Os[u] : 0.0;
+            const double2 hp = make_double2(0.5 * ph[u].x, 0.5 * ph[u].y);
+            const double2 Wa = cmul(make_double2(A + Bp_, Ap - B), hp);
+            const double2 Wb = cmul(make_double2(A - Bp_, Ap + B), cconj(hp));
+            if (m0 + u * NT == 0) {
+                const double2 s0 = cadd(Wa, Wb);
+                xe[swz<S>(pk[u])] = s0; xo[swz<S>(pk[u])] = s0;
+            } else {
+                xe[swz<S>(pk[u])] = Wa; xe[swz<S>(pkc[u])] = Wb;
+                xo[swz<S>(pk[u])] = cmul(Wa, wm[u]); xo[swz<S>(pkc[u])] = cmul(Wb, cconj(wm[u]));
+            }
+        }
+    }
+    __syncthreads();
+    const int tr = tid / C::TPT, lt = tid - tr * C::TPT;               // 0: even longitudes, 1: odd longitudes
+    double2* x = smem2 + (size_t)tr * C::BUF;
+    RowIO io;
+    io.live = b < batch; io.mirror = mirror; io.gs_lon = 2 * gs_lon;
+    io.o1 = grid + (int64_t)b * gs_b + (int64_t)i1 * gs_lat + tr * gs_lon;
+    io.o2 = grid + (int64_t)b * gs_b + (int64_t)(mirror ? i2 : 0) * gs_lat + tr * gs_lon;
+    pass3<C, 0, true, 0>(x, T1, T2, lt, io);
+    tsync<C::TPT>(tr);
+    pass3<C, 1, true, 0>(x, T1, T2, lt, io);
+    tsync<C::TPT>(tr);
+    pass3<C, 2, true, 1>(x, T1, T2, lt, io);
+}
+
+template <class C>
+__global__ void __launch_bounds__(C::NT, 1) k_lon_ana_fft3s2(DevTables t, const int* __restrict__ perm, int batch, const double* __restrict__ grid,
+                                                             int64_t gs_b, int64_t gs_lat, int64_t gs_lon, double* __restrict__ G) {
+    extern __shared__ double2 smem2[];
+    constexpr int K = C::K, NT = C::NT, S = C::S;
+    static_assert(C::NF == 2 && C::NP == 3, "two halves per CTA");
+    double2* T1 = smem2 + (size_t)2 * C::BUF;
+    double2* T2 = T1 + C::T1N;
+    const int N = t.nmax, R = t.nrows;
+    const int row = blockIdx.y, b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int i1 = t.row_i1[row], i2 = t.row_i2[row];
+    const bool mirror = i2 >= 0;
+    const double w1 = t.w1[row], w2 = t.w2[row];
+    const int tr = tid / C::TPT, lt = tid - tr * C::TPT;
+    double2* x = smem2 + (size_t)tr * C::BUF;
+    fill_tables<C, false, 2>(t.tw, T1, T2, tid);
+    {
+        RowIO io;
+        io.live = b < batch; io.mirror = mirror; io.gs_lon = 2 * gs_lon;
+        io.o1 = const_cast<double*>(grid) + (int64_t)b * gs_b + (int64_t)i1 * gs_lat + tr * gs_lon;
+        io.o2 = const_cast<double*>(grid) + (int64_t)b * gs_b + (int64_t)(mirror ? i2 : 0) * gs_lat + tr * gs_lon;
+        __syncthreads();
+        pass3<C, 2, false, 2>(x, T1, T2, lt, io);
+        tsync<C::TPT>(tr);
+        pass3<C, 1, false, 0>(x, T1, T2, lt, io);
+        tsync<C::TPT>(tr);
+        pass3<C, 0, false, 0>(x, T1, T2, lt, io);
+    }
+    __syncthreads();
+    if (b < t.Bp) {
+        const double2* xe = smem2;
+        const double2* xo = smem2 + C::BUF;
+        const bool live = b < batch;
+        const int64_t gstep = (int64_t)R * 2 * t.Gs;
+        double* gcol = G + ((int64_t)row * 2) * t.Gs + colidx(0, b, t.GS);
+        for (int m = tid; m <= N; m += NT) {
+            if (t.mstride > 1 && (m < t.m0 || (m - t.m0) % t.mstride)) continue;       // m-sharding: foreign orders are skipped
+            const int pk = swz<S>(perm[m]), pkc = swz<S>(perm[m ? K - m : 0]);
+            const double2 wm = t.tw[m];                                                // exp(-2 pi i m / 2K)
+            const double2 Wk = cadd(xe[pk], cmul(wm, xo[pk]));
+            const double2 Wc = cconj(cadd(xe[pkc], cmul(cconj(wm), xo[pkc])));
+            const double2 F = make_double2(0.5 * (Wk.x + Wc.x), 0.5 * (Wk.y + Wc.y));
+            const double2 D = csub(Wk, Wc);
+            const double2 Fp = make_double2(0.5 * D.y, -0.5 * D.x);
+            const double2 phc = cconj(t.phase[m]);
+            const double2 Z = cmul(F, phc), Zp = cmul(Fp, phc);
+            const double a = w1 * Z.x, bb = -w1 * Z.y, ap = w2 * Zp.x, bp = -w2 * Zp.y;
+            double* g = gcol + (int64_t)m * gstep;
+            g[0] = live ? a + ap : 0.0; g[t.GS] = live ? bb + bp : 0.0;
+            g[t.Gs] = live ? a - ap : 0.0; g[t.Gs + t.GS] = live ? bb - bp : 0.0;
+        }
+    }
+}
+
 // ---- persistent synthesis kernel: the next work item's G slab streams into shared memory while this one is transformed ------
 // One CTA per SM walks the (latitude pair, field group) items.  What the two-CTA kernel above cannot hide at the long lengths
 // is its input phase (r02 cycle counters at cfg3: 53 % of a CTA's time is the spectrum assembly waiting for G -- registers
@@ -595,8 +726,17 @@ static const Fft3Info* fft3_find(int K) {
     return nullptr;
 }
 
+// rows of twice a listed two-transforms-per-CTA length (8640, 9216, 11520): k_lon_*_fft3s2, any number of fields
+static const Fft3Info* fft3_find_split(int K) {
+    static const int on = getenv("SHB200_FFT3S2") ? atoi(getenv("SHB200_FFT3S2")) : 1;
+    if (!on || K % 2 || fft3_find(K)) return nullptr;
+    const Fft3Info* e = fft3_find(K / 2);
+    return e && e->NF == 2 && e->R2 > 1 ? e : nullptr;
+}
+
 // the three-pass kernels serve plans of >= 8 fields on the listed lengths (their G column groups are NF fields wide)
 bool lon_fft3_plan(int K, int Bp, int* group_size) {
+    if (fft3_find_split(K)) { if (group_size) *group_size = 0; return true; }      // group size: the plan's default
     const Fft3Info* e = fft3_find(K);
     if (!e || Bp < 8) return false;
     if (group_size) *group_size = e->NF >= 4 ? e->NF : 4;
@@ -605,6 +745,7 @@ bool lon_fft3_plan(int K, int Bp, int* group_size) {
 
 void lon_fft3_perm(int K, std::vector<int>& perm) {
     const Fft3Info* e = fft3_find(K);
+    if (!e && (e = fft3_find_split(K))) K /= 2;                                    // table of the half length
     perm.assign(K, 0);
     if (!e) return;
     const int rad[3] = {e->R0, e->R1, e->R2}, ns[3] = {1, e->R0, e->R0 * e->R1};
@@ -667,9 +808,38 @@ static bool fft3p_on() {
     return v != 0;
 }
 
+#define SHB_FFT3S2_CONFIGS(X) X(4320, 16, 18, 15, 2, 256) X(4608, 16, 18, 16, 2, 256) X(5760, 16, 18, 20, 2, 256)
+
+template <class C>
+static int launch_syn3s2(const Plan& p, int batch, double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, cudaStream_t st) {
+    static PerDeviceOnce attr;
+    if (attr.first()) { SHB_CUDA(cudaFuncSetAttribute(fft3::k_lon_syn_fft3s2<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM)); }
+    trace_kernel(p, "k_lon_syn_fft3s2");
+    fft3::k_lon_syn_fft3s2<C><<<dim3(batch, p.nrows), C::NT, C::SMEM, st>>>(p.t, p.fft3_perm, batch, p.G, grid, gs_b, gs_lat, gs_lon);
+    return 0;
+}
+template <class C>
+static int launch_ana3s2(const Plan& p, int batch, const double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, cudaStream_t st) {
+    static PerDeviceOnce attr;
+    if (attr.first()) { SHB_CUDA(cudaFuncSetAttribute(fft3::k_lon_ana_fft3s2<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM)); }
+    trace_kernel(p, "k_lon_ana_fft3s2");
+    // every field of the plan's width is written (zeros beyond the batch): the Legendre stage reads whole column groups
+    fft3::k_lon_ana_fft3s2<C><<<dim3(p.Bp, p.nrows), C::NT, C::SMEM, st>>>(p.t, p.fft3_perm, batch, grid, gs_b, gs_lat, gs_lon, p.G);
+    return 0;
+}
+
 // returns -1 when this path does not apply to the call (the caller then uses lon_fft.cu)
 int launch_lon_syn_fft3(const Plan& p, int batch, double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, cudaStream_t st) {
     if (!p.fft3_perm || gs_b == 1) return -1;
+    if (fft3_find_split(p.K)) {
+        if (4 * p.nmax >= p.K) return -1;                     // aliasing into the other half's bins: the in-place kernels
+        switch (p.K / 2) {
+#define X(KK, A, B, C, NF, TPT) case KK: return launch_syn3s2<fft3::Cfg<KK, A, B, C, NF, TPT>>(p, batch, grid, gs_b, gs_lat, gs_lon, st);
+            SHB_FFT3S2_CONFIGS(X)
+#undef X
+            default: return -1;
+        }
+    }
     if (fft3p_on() && 2 * p.nmax <= p.K && gs_lon == 1) {
         static const int tpt = getenv("SHB200_FFT3P_TPT") ? atoi(getenv("SHB200_FFT3P_TPT")) : 96;
         if (tpt == 128) {
@@ -696,6 +866,15 @@ int launch_lon_syn_fft3(const Plan& p, int batch, double* grid, int64_t gs_b, in
 }
 int launch_lon_ana_fft3(const Plan& p, int batch, const double* grid, int64_t gs_b, int64_t gs_lat, int64_t gs_lon, cudaStream_t st) {
     if (!p.fft3_perm || gs_b == 1) return -1;
+    if (fft3_find_split(p.K)) {
+        if (4 * p.nmax >= p.K) return -1;
+        switch (p.K / 2) {
+#define X(KK, A, B, C, NF, TPT) case KK: return launch_ana3s2<fft3::Cfg<KK, A, B, C, NF, TPT>>(p, batch, grid, gs_b, gs_lat, gs_lon, st);
+            SHB_FFT3S2_CONFIGS(X)
+#undef X
+            default: return -1;
+        }
+    }
     // (one CTA of 4 x 96 threads per SM instead of two of 4 x 64, the shape that helped the persistent synthesis kernel, is slower
     // here: 0.311 -> 0.367 ms at cfg3 -- the two CTAs hide each other's row loads and G stores)
     switch (p.K) {

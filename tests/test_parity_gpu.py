@@ -624,8 +624,8 @@ def _same_kernels(got, want):
 R2_SYN = [("cfg3", "r2_syn_cfg3_b64.npz", ["k_pack_n", "k_leg_syn_tab<4>", "k_lon_syn_fft<static/8>"]),
           ("cfg2", "r2_syn_cfg2_b240.npz", ["k_pack_n", "k_leg_syn_tab<4>", "k_lon_syn_fft<static/8>"]),
           ("n2160", "r2_syn_n2160_b16.npz", ["k_pack_n", "k_leg_syn_tab<1>", "k_lon_syn_fft<static>"]),
-          # shlib's own default grid at nmax 2160 (shlib.pyx:87-92: 5760 x 11520): 57 GB P table, in-place FFT of length 11520
-          ("shlib2160", "r2_syn_shlib2160_b16.npz", ["k_pack_n", "k_leg_syn_tab<1>", "k_lon_syn_fft<runtime>"])]
+          # shlib's own default grid at nmax 2160 (shlib.pyx:87-92: 5760 x 11520): 57 GB P table, rows of 11520 = 2 x 5760 longitudes
+          ("shlib2160", "r2_syn_shlib2160_b16.npz", ["k_pack_n", "k_leg_syn_tab<1>", "k_lon_syn_fft3s2"])]
 
 
 @pytest.mark.parametrize("tag,fname,kernels", R2_SYN)
@@ -666,7 +666,7 @@ R2_ANA = [("cfg3", "r2_ana_cfg3_b64.npz", ["k_lon_ana_fft<static/8>", "k_leg_ana
           ("cfg2", "r2_ana_cfg2_b240.npz", ["k_lon_ana_fft<static/8>", "k_leg_ana_tab<4>", "k_unpack_n"]),
           ("n256", "r2_ana_n256_b4.npz", ["k_lon_ana_fft<runtime>", "k_leg_ana_small", "k_unpack_s"]),
           ("n2160", "r2_ana_n2160_b16.npz", ["k_lon_ana_fft<static>", "k_leg_ana_tab<1>", "k_unpack_n"]),
-          ("shlib2160", "r2_ana_shlib2160_b16.npz", ["k_lon_ana_fft<runtime>", "k_leg_ana_tab<1>", "k_unpack_n"])]
+          ("shlib2160", "r2_ana_shlib2160_b16.npz", ["k_lon_ana_fft3s2", "k_leg_ana_tab<1>", "k_unpack_n"])]
 
 
 @pytest.mark.parametrize("tag,fname,kernels", R2_ANA)
@@ -1164,10 +1164,11 @@ def test_single_field_analysis_kernel_vs_oracle(engine, nmax, gtype, quad):
     assert np.array_equal(engine.analysis(f[1:], nmax, lon, lat, quadrature=quad)[0], engine.analysis(np.ascontiguousarray(f[1:]), nmax, lon, lat, quadrature=quad)[0])
 
 
-@pytest.mark.parametrize("K,kern", [(5760, "fft3"), (11520, "fft<static")])
+@pytest.mark.parametrize("K,kern", [(5760, "fft3"), (11520, "fft3s2")])
 def test_long_regular_grid_rows_vs_oracle(engine, K, kern):
     """Longitude counts of shlib's own regular grids for nmax 513 ... 2160 (shlib.pyx:87-92: 5760 and 11520 points per row):
-    compile-time FFT kernels (three-pass 16 x 18 x 20 for 5760; in-place mixed radix, one transform per CTA, for 11520)."""
+    three-pass 16 x 18 x 20 for 5760; 11520 as one radix-2 step over two three-pass transforms of half the
+    length in one CTA (k_lon_*_fft3s2)."""
     nmax, B = 40, 16
     lon = -180.0 + 180.0 / K + np.arange(K) * (360.0 / K)
     lat = np.array([-89.96875, -45.03125, -0.03125, 0.03125, 45.03125, 89.96875, 12.53125])
