@@ -254,6 +254,11 @@ int shb200_debug_legendre(int32_t device, int32_t nmax, double lat_deg, double* 
  * outermost axis, dense stride of each axis. */
 int shb200_debug_host_copy(int32_t nax, const int64_t* ext, const int64_t* strides, double* host, double* dense, int32_t to_dense, int64_t* info);
 
+/* Debug/test hook (host only, no GPU): the chunk sizes (fields per chunk, at most 8 values) the host entry points cut a call of
+ * `batch` fields into -- which = 0 synthesis, 1 analysis, 2 round trip; chunkable = the batch axis is the slowest axis of every
+ * array of the call.  Returns the number of chunks (> 0) or an error code (< 0). */
+int shb200_debug_host_chunks(int32_t batch, int32_t which, int32_t chunkable, int32_t* sizes);
+
 /* Debug/measurement hook: cycle counters of the three-pass longitude kernels (lon_fft3.cu).  enable != 0 switches the
  * counting on (thread 0 of every CTA adds its clock64 deltas), 0 off; the current sums are copied to out (16 values, may be
  * NULL: synthesis [CTAs, assembly, pass 0, pass 1, last pass + row stores], then analysis [CTAs, table fill, first pass + row

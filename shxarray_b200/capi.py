@@ -22,7 +22,7 @@ EXPORTS = [
     "shb200_version", "shb200_last_error", "shb200_plan_create", "shb200_plan_destroy", "shb200_plan_get_info",
     "shb200_synthesis", "shb200_analysis", "shb200_synthesis_host", "shb200_analysis_host", "shb200_multiply",
     "shb200_gauss_nodes", "shb200_debug_legendre", "shb200_plan_stage_times", "shb200_plan_last_kernels", "shb200_roundtrip_host",
-    "shb200_host_alloc", "shb200_host_free", "shb200_host_trim", "shb200_debug_host_copy",
+    "shb200_host_alloc", "shb200_host_free", "shb200_host_trim", "shb200_debug_host_copy", "shb200_debug_host_chunks",
     "shb200_shard_size", "shb200_analysis_packed", "shb200_unpack_shards", "shb200_scatter_rows", "shb200_apply_mask",
     "shb200_gfc_parse", "shb200_parse_floats", "shb200_scatter_nm", "shb200_polygon_mask", "shb200_debug_fft_cycles",
     "shb200_peer_alloc", "shb200_peer_open", "shb200_peer_close", "shb200_peer_free", "shb200_push_rows",
@@ -98,6 +98,7 @@ def lib():
     L.shb200_host_trim.argtypes = []
     L.shb200_debug_fft_cycles.argtypes = [i32, vp]
     L.shb200_debug_host_copy.argtypes = [i32, vp, vp, vp, vp, i32, vp]
+    L.shb200_debug_host_chunks.argtypes = [i32, i32, i32, vp]
     L.shb200_shard_size.argtypes = [i32, i32, i32]
     L.shb200_analysis_packed.argtypes = [vp, i32, vp, i64, i64, i64, vp, i64, vp, po]
     L.shb200_unpack_shards.argtypes = [i32, i32, i32, vp, i64, i64, vp, i64, i64, vp]

@@ -386,6 +386,37 @@ static int copy_out_bounced(HostIO& h, const ChunkView& v, OutRing& r) {
 // chunks of at least 16 fields: below 32 columns the Legendre stage leaves the tensor-core kernels
 static int host_chunks(int batch) { return std::max(1, std::min(4, batch / 16)); }
 
+// Chunk sizes of one host call: up to 4 equal chunks of whole 8-field groups; the chunk at the exposed end of the pipeline --
+// the FIRST of a synthesis (nothing travels back before its grid exists), the LAST of an analysis (its coefficients travel back
+// after everything else), both for the round trip -- is cut into 8 + 8 + rest fields, which shortens the un-overlapped head /
+// tail of the call (SHB200_HOST_EDGE_SPLIT=0: equal chunks only).  which = 0 synthesis, 1 analysis, 2 round trip; chunkable:
+// the batch axis is the slowest axis of every array of the call.  At most 4 + 2 + 2 = HostIO::MAXCH chunks.
+static std::vector<int> host_chunk_plan(int batch, int which, bool chunkable) {
+    std::vector<int> nbs;
+    int nchunk = chunkable ? host_chunks(batch) : 1;
+    const int per = nchunk == 1 ? batch : ((batch + nchunk - 1) / nchunk + 7) / 8 * 8;
+    for (int b0 = 0; b0 < batch; b0 += per) nbs.push_back(std::min(per, batch - b0));
+    static const bool edge_split = [] { const char* e = getenv("SHB200_HOST_EDGE_SPLIT"); return !e || atoi(e) != 0; }();
+    auto split = [&](size_t at, bool small_first) {
+        const int nb = nbs[at];
+        if (nb <= 8) return;
+        std::vector<int> parts;
+        if (small_first) {
+            if (nb >= 24) parts = {8, 8, nb - 16}; else parts = {8, nb - 8};
+        } else {                                         // chunk boundaries stay multiples of 8 fields: the tail takes the remainder
+            const int last = nb % 8 ? nb % 8 : 8, rest = nb - last;
+            if (rest >= 16) parts = {rest - 8, 8, last}; else parts = {rest, last};
+        }
+        nbs.erase(nbs.begin() + at);
+        nbs.insert(nbs.begin() + at, parts.begin(), parts.end());
+    };
+    if (edge_split && nbs.size() > 1) {
+        if (which == 1 || which == 2) split(nbs.size() - 1, false);
+        if (which == 0 || which == 2) split(0, true);
+    }
+    return nbs;
+}
+
 // The pipeline.  which = 0: synthesis (in = coefficients, out = grid); 1: analysis (in = grid, out = coefficients);
 // 2: round trip (in = coefficients, mid = grid written to the host AND read back from it, out = coefficients).
 struct HostCall {
@@ -425,31 +456,7 @@ static int run_host_call(HostCall& c) {
         if ((rc = ensure_stage(h, out_stage, c.out.full.total))) return rc;
         c.in.dev = h.stage[in_stage]; c.out.dev = h.stage[out_stage];
     }
-    // chunk sizes: up to 4 equal chunks of whole 8-field groups; the chunk at the exposed end of the pipeline -- the FIRST of a
-    // synthesis (nothing travels back before its grid exists), the LAST of an analysis (its coefficients travel back after
-    // everything else), both for the round trip -- is cut into 8 + 8 + rest fields, which shortens the un-overlapped head /
-    // tail of the call (SHB200_HOST_EDGE_SPLIT=0: equal chunks only)
-    std::vector<int> nbs;
-    {
-        int nchunk = host_chunks(c.batch);
-        if (!(c.in.batch_outer && c.out.batch_outer && (!rt || c.mid.batch_outer))) nchunk = 1;
-        const int per = nchunk == 1 ? c.batch : ((c.batch + nchunk - 1) / nchunk + 7) / 8 * 8;
-        for (int b0 = 0; b0 < c.batch; b0 += per) nbs.push_back(std::min(per, c.batch - b0));
-        static const bool edge_split = [] { const char* e = getenv("SHB200_HOST_EDGE_SPLIT"); return !e || atoi(e) != 0; }();
-        auto split = [&](size_t at, bool small_first) {
-            const int nb = nbs[at];
-            if (nb < 16) return;
-            std::vector<int> parts;
-            if (nb >= 24) parts = small_first ? std::vector<int>{8, 8, nb - 16} : std::vector<int>{nb - 16, 8, 8};
-            else parts = small_first ? std::vector<int>{8, nb - 8} : std::vector<int>{nb - 8, 8};
-            nbs.erase(nbs.begin() + at);
-            nbs.insert(nbs.begin() + at, parts.begin(), parts.end());
-        };
-        if (edge_split && nbs.size() > 1) {
-            if (c.which == 1 || rt) split(nbs.size() - 1, false);
-            if (c.which == 0 || rt) split(0, true);
-        }
-    }
+    std::vector<int> nbs = host_chunk_plan(c.batch, c.which, c.in.batch_outer && c.out.batch_outer && (!rt || c.mid.batch_outer));
     const int nchunk = (int)nbs.size();        // <= 4 + 2 + 2 = HostIO::MAXCH
     // an 8-field chunk of a tensor-core plan runs 32 columns wide (half of them zero): it stays on the kernels of its neighbours
     if (p.dmma && p.Bp >= 16) c.o_syn.min_fields = c.o_ana.min_fields = 16;
@@ -665,6 +672,13 @@ int shb200_roundtrip_host(shb200_plan* plan, int32_t batch, const double* coef, 
     coef_array(c.out, batch, (int64_t)(p.nmax + 1) * (p.nmax + 1), coef_out, os_b, os_nm);
     std::lock_guard<std::mutex> lock(p.mu);
     return run_host_call(c);
+}
+
+int shb200_debug_host_chunks(int32_t batch, int32_t which, int32_t chunkable, int32_t* sizes) {
+    if (batch < 1 || which < 0 || which > 2 || !sizes) { set_error("debug_host_chunks: invalid argument"); return SHB200_EINVAL; }
+    const std::vector<int> nbs = host_chunk_plan(batch, which, chunkable != 0);
+    for (size_t i = 0; i < nbs.size() && i < (size_t)HostIO::MAXCH; ++i) sizes[i] = nbs[i];
+    return (int)nbs.size();
 }
 
 int shb200_debug_host_copy(int32_t nax, const int64_t* ext, const int64_t* strides, double* host, double* dense, int32_t to_dense, int64_t* info) {

@@ -235,3 +235,33 @@ def test_plan_cache_digest_memo_sees_in_place_changes():
     e0 = _digest(big)
     big[123456] += 1
     assert _digest(big) != e0
+
+
+def test_host_pipeline_chunk_plan():
+    """Chunk sizes of the host entry points (host_io.cu: host_chunk_plan, through shb200_debug_host_chunks; no GPU): whole
+    8-field groups that cover the batch exactly, at most 8 chunks, one chunk when the batch axis is not the slowest, and the
+    exposed end of the pipeline (first chunk of a synthesis, last of an analysis, both for a round trip) cut down to 8 fields."""
+    def plan(batch, which, chunkable=True):
+        sizes = np.zeros(8, dtype=np.int32)
+        n = capi.lib().shb200_debug_host_chunks(batch, which, int(chunkable), sizes.ctypes.data)
+        assert 1 <= n <= 8, (batch, which, n)
+        return [int(v) for v in sizes[:n]]
+
+    for batch in list(range(1, 140)) + [240, 256, 500, 1000]:
+        for which in (0, 1, 2):
+            s = plan(batch, which)
+            assert sum(s) == batch and all(v > 0 for v in s)
+            assert all(v % 8 == 0 for v in s[:-1]) or len(s) == 1            # every chunk but the last is whole 8-field groups
+            if batch < 32:
+                assert s == [batch]                                           # too few fields to overlap copies and kernels
+            else:
+                if which in (0, 2):
+                    assert s[0] == 8                                          # head of the pipeline
+                if which in (1, 2):
+                    assert s[-1] == (batch % 8 or 8)                          # tail of the pipeline: the remainder, at most 8 fields
+            assert plan(batch, which, chunkable=False) == [batch]
+    assert plan(64, 0) == [8, 8, 16, 16, 16] and plan(64, 1) == [16, 16, 16, 8, 8] and plan(64, 2) == [8, 8, 16, 16, 8, 8]
+    assert plan(128, 2) == [8, 8, 16, 32, 32, 16, 8, 8]
+    sizes = np.zeros(8, dtype=np.int32)
+    assert capi.lib().shb200_debug_host_chunks(0, 0, 1, sizes.ctypes.data) < 0
+    assert capi.lib().shb200_debug_host_chunks(8, 3, 1, sizes.ctypes.data) < 0
