@@ -1186,3 +1186,34 @@ def test_long_regular_grid_rows_vs_oracle(engine, K, kern):
     # the oracle's row weight is weight * cos(lat * pi/180) (analysis.pyx:121,129): the same numbers to an ulp
     aref = O.analysis(g[:1], nmax, lon, lat, kind="port", weight=1e-3)
     assert per_field_err(a[:1], aref) <= TOL
+
+
+@pytest.mark.parametrize("nmax,B,gtype", [(720, 2, "gauss"), (400, 1, "regular")])
+def test_polar_skipping_seeds_of_the_recursion_kernels(nmax, B, gtype):
+    """Tiny-batch plans have no P table; their synthesis kernel (k_leg_syn_dfma) starts the recursion of a block of rows at the
+    first 32-degree chunk in which some |P_nm| reaches 1e-24, from the state (p1, p2) stored for that chunk at plan creation.
+    Against the same kernel visiting everything (SHB200_FLAG_NO_POLAR_SKIP): far below the contract; against the oracle on a
+    subset of rows including the polar ones; the visited fraction is reported."""
+    import torch
+    g = sb.lonlat_grid(nmax, gtype=gtype)
+    lon, lat = g["lon"], g["lat"]
+    c = S.random_coefficients(nmax, B, kaula=False, seed=321)
+    ct = torch.from_numpy(c).cuda()
+    nsh = (nmax + 1) ** 2
+    res = {}
+    for tag, flags in (("skip", 0), ("all", capi.FLAG_NO_POLAR_SKIP)):
+        plan = capi.Plan(nmax, lat, lon, max_batch=B, flags=flags)
+        f = torch.empty((B, len(lat), len(lon)), dtype=torch.float64, device="cuda")
+        plan.synthesis_dev(B, ct.data_ptr(), nsh, 1, f.data_ptr(), f.stride(0), f.stride(1), 1, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert plan.last_kernels()[1] == "k_leg_syn_dfma", plan.last_kernels()
+        res[tag] = (f.cpu().numpy(), plan.info.legendre_visited_synthesis)
+        plan.close()
+    assert res["all"][1] == 1.0 and 0.5 < res["skip"][1] < 0.97, (res["all"][1], res["skip"][1])
+    assert per_field_err(res["skip"][0], res["all"][0]) <= 1e-13
+    rows = np.array([0, 1, 5, len(lat) // 3, len(lat) // 2, len(lat) - 2, len(lat) - 1])
+    n, m = sb.nm_index(nmax)
+    ref = np.moveaxis(O.synthesis(c, n, m, lon[::41], lat[rows], kind="port"), 2, 0)
+    fmax = np.abs(res["skip"][0]).reshape(B, -1).max(axis=1)
+    err = np.abs(res["skip"][0][:, rows][:, :, ::41] - ref).reshape(B, -1).max(axis=1) / fmax
+    assert err.max() <= TOL
