@@ -101,6 +101,7 @@ void lon_fft_perm(int K, int Bp, std::vector<int>& perm);
 // three-pass composite-radix kernels (lon_fft3.cu)
 bool lon_fft3_plan(int K, int Bp, int* group_size);
 int build_syn_seeds(Plan& p, double* visited);      // legendre_dfma.cu
+int build_ana_seeds(Plan& p, double* visited);
 // fused point-mode synthesis (points.cu)
 bool points_fused_wanted(int npoints);
 void launch_syn_points(const Plan& p, int batch, double* out, int64_t gs_b, int64_t gs_pt, cudaStream_t st);
@@ -153,7 +154,8 @@ struct Plan {
     double* G = nullptr;    // [(nmax+1)][nrows][2][Gs] (+64 slack rows)
     double* Ptab = nullptr; // tiled device-resident P_nm table (legendre_tab.cu) or null
     const int* syn_seed_k0 = nullptr; const double2* syn_seed_state = nullptr; int syn_seed_rows = 0;   // polar-skipping seeds of k_leg_syn_dfma (legendre_dfma.cu)
-    double seed_visited_syn = 1.0;
+    const int* ana_seed_k0 = nullptr; const double2* ana_seed_state = nullptr; int ana_seed_rows = 0;   // ... of k_leg_ana_one
+    double seed_visited_syn = 1.0, seed_visited_ana = 1.0;
     mutable double* ana_scratch = nullptr; mutable size_t ana_scratch_bytes = 0;   // per-tile partial sums of k_leg_ana_small (split mode), grown on first use
     int Rpad = 0;
     // polar skipping (table kernels): tile lists of the persistent synthesis kernel, heaviest tile first, for its three tile

@@ -390,6 +390,7 @@ static int build_plan(const shb200_plan_desc& d, Plan& p) {
     // tiny-batch plans (recursion kernels): polar-skipping seeds for the synthesis kernel
     if (p.NC < 32 && d.mode == SHB200_MODE_GRID && !(d.flags & SHB200_FLAG_NO_POLAR_SKIP) && N >= 256) {
         if ((rc = build_syn_seeds(p, &p.seed_visited_syn))) return rc;
+        if (d.quadrature != SHB200_QUAD_NONE && p.NC <= 24 && (rc = build_ana_seeds(p, &p.seed_visited_ana))) return rc;     // single-field analysis kernel
     }
     if (d.flags & SHB200_FLAG_TIMING)
         for (int i = 0; i < 8; ++i) SHB_CUDA(cudaEventCreate(&p.ev[i]));
@@ -659,7 +660,7 @@ int shb200_plan_get_info(const shb200_plan* plan, shb200_plan_info* info) {
     info->launches_synthesis = p.launches_syn; info->launches_analysis = p.launches_ana;
     const int shape = p.NC > 64 ? 0 : (p.NC > 32 ? 1 : 2);      // tile shape of a full-width call (legendre_tab.cu)
     info->legendre_visited_synthesis = p.Ptab && p.t.first_blk ? p.visited_syn[shape] : p.seed_visited_syn;
-    info->legendre_visited_analysis = p.Ptab && p.t.first_blk ? p.visited_ana[shape] : 1.0;
+    info->legendre_visited_analysis = p.Ptab && p.t.first_blk ? p.visited_ana[shape] : p.seed_visited_ana;
     return 0;
 }
 

@@ -1188,32 +1188,57 @@ def test_long_regular_grid_rows_vs_oracle(engine, K, kern):
     assert per_field_err(a[:1], aref) <= TOL
 
 
-@pytest.mark.parametrize("nmax,B,gtype", [(720, 2, "gauss"), (400, 1, "regular")])
+@pytest.mark.parametrize("nmax,B,gtype", [(720, 2, "gauss"), (400, 1, "regular"), (300, 1, "fine")])
 def test_polar_skipping_seeds_of_the_recursion_kernels(nmax, B, gtype):
-    """Tiny-batch plans have no P table; their synthesis kernel (k_leg_syn_dfma) starts the recursion of a block of rows at the
-    first 32-degree chunk in which some |P_nm| reaches 1e-24, from the state (p1, p2) stored for that chunk at plan creation.
-    Against the same kernel visiting everything (SHB200_FLAG_NO_POLAR_SKIP): far below the contract; against the oracle on a
-    subset of rows including the polar ones; the visited fraction is reported."""
+    """Tiny-batch plans have no P table; their synthesis kernel (k_leg_syn_dfma) and the single-field analysis kernel
+    (k_leg_ana_one) start the recursion of a block of rows at the first chunk in which some |P_nm| reaches 1e-24, from the state
+    (p1, p2) stored for that chunk at plan creation.  Against the same kernels visiting everything (SHB200_FLAG_NO_POLAR_SKIP):
+    far below the contract; against the oracle (synthesis on a subset of rows including the polar ones, analysis of a grid
+    that is non-zero on a few rows only); the visited fractions are reported."""
     import torch
-    g = sb.lonlat_grid(nmax, gtype=gtype)
+    if gtype == "fine":       # 720 mirror pairs: the analysis kernel then has two row tiles, the polar one skips
+        g = dict(lon=np.arange(768) * (360.0 / 768), lat=-90 + 0.0625 + 0.125 * np.arange(1440))
+    else:
+        g = sb.lonlat_grid(nmax, gtype=gtype)
     lon, lat = g["lon"], g["lat"]
     c = S.random_coefficients(nmax, B, kaula=False, seed=321)
     ct = torch.from_numpy(c).cuda()
     nsh = (nmax + 1) ** 2
+    q = dict(quadrature=capi.QUAD_LATWEIGHTS, weight=1.0 / (2 * len(lon)), lat_weights=g["lat_weights"]) if gtype == "gauss" else \
+        dict(quadrature=capi.QUAD_SHLIB, weight=float(sb.analysis_weight_shlib(lon, lat)))
+    rows = np.array([0, 1, 5, len(lat) // 3, len(lat) // 2, len(lat) - 2, len(lat) - 1])
+    gsub = np.zeros((1, len(lat), len(lon)))
+    gsub[0, rows[:, None], np.arange(0, len(lon), 41)[None, :]] = np.random.default_rng(8).standard_normal((len(rows), len(range(0, len(lon), 41))))
+    gfull = np.random.default_rng(9).standard_normal((1, len(lat), len(lon)))
     res = {}
     for tag, flags in (("skip", 0), ("all", capi.FLAG_NO_POLAR_SKIP)):
-        plan = capi.Plan(nmax, lat, lon, max_batch=B, flags=flags)
+        plan = capi.Plan(nmax, lat, lon, max_batch=B, flags=flags, **q)
+        st = torch.cuda.current_stream().cuda_stream
         f = torch.empty((B, len(lat), len(lon)), dtype=torch.float64, device="cuda")
-        plan.synthesis_dev(B, ct.data_ptr(), nsh, 1, f.data_ptr(), f.stride(0), f.stride(1), 1, torch.cuda.current_stream().cuda_stream)
+        plan.synthesis_dev(B, ct.data_ptr(), nsh, 1, f.data_ptr(), f.stride(0), f.stride(1), 1, st)
         torch.cuda.synchronize()
         assert plan.last_kernels()[1] == "k_leg_syn_dfma", plan.last_kernels()
-        res[tag] = (f.cpu().numpy(), plan.info.legendre_visited_synthesis)
+        outs = []
+        for src in (gsub, gfull):
+            gt = torch.from_numpy(src).cuda()
+            a = torch.empty((1, nsh), dtype=torch.float64, device="cuda")
+            plan.analysis_dev(1, gt.data_ptr(), gt.stride(0), gt.stride(1), 1, a.data_ptr(), nsh, 1, st)
+            torch.cuda.synchronize()
+            assert plan.last_kernels()[1] == "k_leg_ana_one", plan.last_kernels()
+            outs.append(a.cpu().numpy())
+        res[tag] = (f.cpu().numpy(), plan.info.legendre_visited_synthesis, outs, plan.info.legendre_visited_analysis)
         plan.close()
     assert res["all"][1] == 1.0 and 0.5 < res["skip"][1] < 0.97, (res["all"][1], res["skip"][1])
+    # one row tile from pole to equator (362 / 360 pairs) cannot skip anything; two tiles can
+    assert res["all"][3] == 1.0 and 0.5 < res["skip"][3] <= (0.99 if gtype == "fine" else 1.0), (res["all"][3], res["skip"][3])
     assert per_field_err(res["skip"][0], res["all"][0]) <= 1e-13
-    rows = np.array([0, 1, 5, len(lat) // 3, len(lat) // 2, len(lat) - 2, len(lat) - 1])
+    for a_skip, a_all in zip(res["skip"][2], res["all"][2]):
+        assert per_field_err(a_skip, a_all) <= 1e-13
     n, m = sb.nm_index(nmax)
     ref = np.moveaxis(O.synthesis(c, n, m, lon[::41], lat[rows], kind="port"), 2, 0)
     fmax = np.abs(res["skip"][0]).reshape(B, -1).max(axis=1)
     err = np.abs(res["skip"][0][:, rows][:, :, ::41] - ref).reshape(B, -1).max(axis=1) / fmax
     assert err.max() <= TOL
+    if gtype != "gauss":          # the oracle integrates with shlib's weights: the sum over the non-zero subset (analysis.pyx:125-139)
+        aref = O.analysis(gsub[:, rows][:, :, ::41], nmax, lon[::41], lat[rows], kind="port", weight=q["weight"])
+        assert per_field_err(res["skip"][2][0], aref) <= TOL
