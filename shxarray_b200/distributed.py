@@ -66,9 +66,36 @@ def _lat_shard_indices(lat, world, rank):
             units.append((i, mate))
         else:
             units.append((i,))
-    lo, hi = shard_bounds(len(units), world, rank)
+    lo, hi = work_bounds([_row_work(lat[u[0]], world) for u in units], world, rank)
     idx = sorted(k for u in units[lo:hi] for k in u)
     return np.asarray(idx, dtype=np.int64)
+
+
+def _row_work(lat_deg, world=1):
+    """Relative cost of a latitude row for a rank of a latitude-sharded transform.  Legendre stage: polar skipping (table kernels
+    and seeded recursion kernels alike) leaves out the degrees n below ~m / cos(lat) of every order m, so a row costs about
+    cos(lat) of an equatorial one plus a floor for the 1e-24 margin -- one nmax-2160 field visits 74 % of the triples, i.e.
+    0.28 + 0.72 cos(lat) averaged over the rows.  Longitude stage and row exchange cost the same for every row: measured on the
+    single-field nmax-2160 synthesis, 9 % of an equatorial row's Legendre time for the FFT and 4.5 % per peer for the NVLink
+    stores of `shb200_push_rows` (`profiles/r02_multigpu_breakdown_n8.json`)."""
+    return 0.28 + 0.72 * abs(np.cos(float(lat_deg) * np.pi / 180.0)) + 0.09 + 0.045 * (int(world) - 1)
+
+
+def work_bounds(weights, world, rank):
+    """Contiguous partition of the units into ``world`` runs of (nearly) equal total weight; every rank gets at least one unit
+    when there are enough.  Equal weights reproduce shard_bounds."""
+    n, world = len(weights), int(world)
+    if n <= world or len(set(weights)) == 1:
+        return shard_bounds(n, world, rank)
+    cum = np.concatenate([[0.0], np.cumsum(np.asarray(weights, dtype=np.float64))])
+    cuts = [0]
+    for r in range(1, world):
+        k = int(np.searchsorted(cum, cum[-1] * r / world, side="left"))
+        if k > 0 and abs(cum[k - 1] - cum[-1] * r / world) <= abs(cum[k] - cum[-1] * r / world):
+            k -= 1                                    # the nearer of the two candidate cuts
+        cuts.append(min(max(k, cuts[-1] + 1), n - (world - r)))
+    cuts.append(n)
+    return cuts[rank], cuts[rank + 1]
 
 
 # ---- exchange formats (numpy definitions; the CUDA kernels of csrc/shard.cu implement the same) -----------------------
