@@ -116,3 +116,26 @@ def test_world2_gloo_sharded_transforms():
     assert [(r[1], r[2]) for r in res] == [(0, 3), (3, 5)]
     for r in res:
         assert r[3] and r[4] and r[5], r
+
+
+def test_work_bounds_balance_contiguous_runs():
+    """Latitude bands of a sharded transform are contiguous runs of (nearly) equal total weight (distributed.work_bounds): they
+    cover every unit once, no rank is empty, equal weights give shard_bounds, and on the 5' grid the polar rank of 8 owns more
+    rows than the equatorial one while the modelled work per rank stays within 2 % of the mean."""
+    from shxarray_b200.distributed import work_bounds, _row_work
+    rng = np.random.default_rng(4)
+    for n, world in ((10, 3), (37, 8), (1080, 8), (5, 5), (3, 8)):
+        w = list(rng.uniform(0.2, 1.0, n))
+        cuts = [work_bounds(w, world, r) for r in range(world)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == n
+        assert all(cuts[r][1] == cuts[r + 1][0] for r in range(world - 1))
+        if n >= world:
+            assert all(hi > lo for lo, hi in cuts)
+        assert [work_bounds([1.0] * n, world, r) for r in range(world)] == [shard_bounds(n, world, r) for r in range(world)]
+    d = 1.0 / 12
+    h = np.arange(d / 2, 90, d)
+    lat = np.concatenate([-h[::-1], h])
+    sizes = [len(lat_shard_indices(lat, 8, r)) for r in range(8)]
+    work = [sum(_row_work(lat[i], 8) for i in lat_shard_indices(lat, 8, r)) for r in range(8)]
+    assert sum(sizes) == len(lat) and sizes[0] > sizes[-1] * 1.5
+    assert max(work) / (sum(work) / 8) < 1.02 and min(work) / (sum(work) / 8) > 0.98
