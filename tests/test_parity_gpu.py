@@ -1242,3 +1242,44 @@ def test_polar_skipping_seeds_of_the_recursion_kernels(nmax, B, gtype):
     if gtype != "gauss":          # the oracle integrates with shlib's weights: the sum over the non-zero subset (analysis.pyx:125-139)
         aref = O.analysis(gsub[:, rows][:, :, ::41], nmax, lon[::41], lat[rows], kind="port", weight=q["weight"])
         assert per_field_err(res["skip"][2][0], aref) <= TOL
+
+
+def test_single_field_nmax2160_analysis_vs_ref_golden():
+    """BASELINE config 4 (one nmax-2160 field on the 5' grid) through the single-field analysis kernel WITH its polar-skipping
+    seeds active (three 360-row tiles), against the oracle/_ref golden of the headline test (field 0 of r2_ana_n2160_b16) and
+    against the exact-argument port on exactly representable longitudes (see test_r2_analysis_headline_kernels_vs_oracle for
+    why the first comparison carries shlib's own trig-argument bound of 4e-12 at nmax 2160)."""
+    import torch
+    z = np.load(os.path.join(GOLDEN, "r2_ana_n2160_b16.npz"))
+    nmax, B16, seed = int(z["nmax"]), int(z["B"]), int(z["seed"])
+    lon, lat = _r2_grid("n2160", z)
+    rows, cols = z["rows"], z["cols"]
+    vals = np.random.default_rng(seed).standard_normal((B16, len(rows), len(cols)))[:1]
+    plan = capi.Plan(nmax, lat, lon, max_batch=1, quadrature=capi.QUAD_SHLIB, weight=float(z["weight"]))
+    assert 0.5 < plan.info.legendre_visited_analysis < 0.95 and 0.5 < plan.info.legendre_visited_synthesis < 0.9
+    grid = torch.zeros((1, len(lat), len(lon)), dtype=torch.float64, device="cuda")
+    ri = torch.as_tensor(rows, device="cuda")[:, None]
+    grid[:, ri, torch.as_tensor(cols, device="cuda")[None, :]] = torch.from_numpy(vals).cuda()
+    nsh = (nmax + 1) ** 2
+    out = torch.empty((1, nsh), dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    plan.analysis_dev(1, grid.data_ptr(), grid.stride(0), grid.stride(1), 1, out.data_ptr(), nsh, 1, st)
+    torch.cuda.synchronize()
+    assert plan.last_kernels()[1] == "k_leg_ana_one", plan.last_kernels()
+    got = out[:, torch.as_tensor(z["positions"], device="cuda")].cpu().numpy()
+    err = np.abs(got - z["values"][:1]).max(axis=1) / z["fieldmax"][:1]
+    assert err.max() <= 4e-12, err
+    cols2 = 135 * np.arange(0, 32, 2)
+    vals2 = np.random.default_rng(seed + 5).standard_normal((1, len(rows), len(cols2)))
+    grid.zero_()
+    grid[:, ri, torch.as_tensor(cols2, device="cuda")[None, :]] = torch.from_numpy(vals2).cuda()
+    plan.analysis_dev(1, grid.data_ptr(), grid.stride(0), grid.stride(1), 1, out.data_ptr(), nsh, 1, st)
+    torch.cuda.synchronize()
+    O.set_exact_trig(True)
+    try:
+        ex = O.analysis(vals2, nmax, lon[cols2], lat[rows], kind="port", weight=float(z["weight"]), nthreads=O.max_threads())
+    finally:
+        O.set_exact_trig(False)
+    ex_err = np.abs(out.cpu().numpy() - ex).max(axis=1) / np.abs(ex).max(axis=1)
+    assert ex_err.max() <= TOL, ("exact-argument port", ex_err)
+    plan.close()
